@@ -1,0 +1,74 @@
+// dsc_internal.h -- context and helpers shared by the engine's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/dsc.h"
+#include "dsc_math.cuh"
+
+struct dsc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int l2_bytes = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    int64_t launches = 0;
+    int timing = 0;
+    float last_ms = -1.0f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // K1 scratch
+    uint32_t *keys = nullptr;        // [keys_slots][cells] order-preserving keys (zero == empty)
+    size_t keys_bytes = 0;
+    int64_t *d_offsets = nullptr;    // device copy of the caller's offsets
+    size_t d_offsets_cap = 0;        // in elements
+    int64_t *h_offsets = nullptr;    // pinned staging for offsets
+    size_t h_offsets_cap = 0;
+    uint32_t *minmax = nullptr;      // [n][2] key-encoded per-grid min / max for normalise
+    size_t minmax_cap = 0;           // in grids
+    int *work_counter = nullptr;     // persistent-kernel tile cursor
+
+    // host-path pipeline: H2D stream -> kernel stream -> D2H stream, double buffered
+    cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    void *stage_pts[2] = {nullptr, nullptr};
+    size_t stage_pts_cap = 0;
+    float *stage_out[2] = {nullptr, nullptr};
+    float *stage_norm[2] = {nullptr, nullptr};
+    dsc_scan_stats *stage_stats[2] = {nullptr, nullptr};
+    int64_t *stage_doff[2] = {nullptr, nullptr};   // device offsets per buffer
+    int64_t *stage_hoff[2] = {nullptr, nullptr};   // pinned offsets per buffer
+    size_t stage_scans_cap = 0;
+    size_t stage_cells = 0;
+
+    // polar tables (K2/K3/K5)
+    int tab_R = 0, tab_S = 0;
+    double *d_rc = nullptr, *d_cos = nullptr, *d_sin = nullptr;
+
+    // generic device scratch for K2/K3 (counts, offsets, temp copies of host inputs)
+    void *scratch = nullptr;
+    size_t scratch_cap = 0;
+};
+
+#define DSC_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+            return DSC_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define DSC_FAIL(ctx, code, msg)                                                              \
+    do {                                                                                      \
+        (ctx)->err = (msg);                                                                   \
+        return (code);                                                                        \
+    } while (0)
+
+// grows ctx->scratch to at least `bytes`
+int dsc_reserve_scratch(dsc_ctx *ctx, size_t bytes);
+// checks the launch that was just issued
+int dsc_check_launch(dsc_ctx *ctx, const char *what);

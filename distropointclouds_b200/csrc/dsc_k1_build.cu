@@ -1,0 +1,537 @@
+// dsc_k1_build.cu -- K1: packed point stream -> scan-context grids (+ K4 normalise).
+//
+// Replaces ScanContext.load_velo_scan + ptcloud2sc_vectorized (scaner_version2.py:57-115) and
+// ScanContextComputer._scan_context (scan_context_node.py:102-157).
+//
+// Data layout in HBM
+//   pts      packed float32 [x,y,z,i] rows, 16 B each (the .bin layout), all scans back to back;
+//            read exactly once with 128-bit streaming loads
+//   keys     scratch uint32 [slots][R*S]: per-cell max of the order-preserving key of z
+//            (0 == empty).  Lives in L2 between the build and decode kernels of a chunk.
+//   out      float32 [n][R][S]: written exactly once, 128-bit coalesced stores
+//
+// Algorithmic bytes per scan: 16*N + 4*R*S  (SURVEY 8d).
+#include "dsc_internal.h"
+
+namespace {
+
+using dsc::BinCfg;
+using dsc::BinResult;
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_PPT = 8;                       // points per thread per tile
+constexpr int K1_TILE = K1_THREADS * K1_PPT;    // 2048 points = 32 KB of stream per CTA
+
+__device__ __forceinline__ float4 ld_stream_f4(const void *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f1(const void *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+struct StatAcc {
+    unsigned nonfinite = 0, overflow = 0, clamped = 0, oor = 0, slow = 0;
+};
+
+__device__ __forceinline__ void flush_stats(const StatAcc &a, unsigned long long *st, int64_t n_in_tile,
+                                            bool first_tile_thread)
+{
+    // st layout == dsc_scan_stats: n_points, n_nonfinite, n_sector_overflow, n_clamped_ring,
+    // n_out_of_range, n_slow_path
+    unsigned v0 = __reduce_add_sync(0xffffffffu, a.nonfinite);
+    unsigned v1 = __reduce_add_sync(0xffffffffu, a.overflow);
+    unsigned v2 = __reduce_add_sync(0xffffffffu, a.clamped);
+    unsigned v3 = __reduce_add_sync(0xffffffffu, a.oor);
+    unsigned v4 = __reduce_add_sync(0xffffffffu, a.slow);
+    if ((threadIdx.x & 31) == 0) {
+        if (v4) atomicAdd(st + 5, (unsigned long long)v4);
+        if (v0) atomicAdd(st + 1, (unsigned long long)v0);
+        if (v1) atomicAdd(st + 2, (unsigned long long)v1);
+        if (v2) atomicAdd(st + 3, (unsigned long long)v2);
+        if (v3) atomicAdd(st + 4, (unsigned long long)v3);
+    }
+    if (first_tile_thread) atomicAdd(st + 0, (unsigned long long)n_in_tile);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void accumulate_point(const BinCfg &cfg, float x, float y, float z,
+                                                 uint32_t *grid, StatAcc &acc)
+{
+    BinResult b;
+    if constexpr (FAST) {
+        bool slow;
+        b = dsc::bin_screened(cfg, x, y, z, 0.0f, 0.0f, &slow);
+        if (slow) {            // too close to a bin boundary (or not finite): redo with the fdlibm chain
+            b = dsc::bin_exact(cfg, x, y, z);
+            acc.slow++;
+        }
+    } else {
+        b = dsc::bin_exact(cfg, x, y, z);
+    }
+    if (b.status > dsc::PT_CLAMPED) {
+        acc.nonfinite += (b.status == dsc::PT_NONFINITE);
+        acc.overflow += (b.status == dsc::PT_SECTOR_OVERFLOW);
+        acc.oor += (b.status == dsc::PT_OUT_OF_RANGE);
+        return;
+    }
+    acc.clamped += (b.status == dsc::PT_CLAMPED);
+    const float zv = b.z;
+    if (zv != zv) return;                          // NaN never wins (scaner_version2.py:107)
+    if (!cfg.full_height && !(zv > 0.0f)) return;  // offset mode: cells start at 0, strict '>'
+    const uint32_t key = dsc::float_to_key(zv);
+    if (key <= 0x007fffffu) return;                // -inf can never beat the -inf init
+    atomicMax(grid + b.cell, key);
+}
+
+// One CTA per (tile, scan): 2048 points -> RED.MAX on the scan's key grid.
+template <bool STRIDE16, bool FAST>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_build_keys(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int scan_base,
+              uint32_t *__restrict__ keys, unsigned long long *__restrict__ stats, int stride_bytes,
+              BinCfg cfg)
+{
+    const int scan_local = blockIdx.y;
+    const int scan = scan_base + scan_local;
+    const int64_t p0 = offsets[scan];
+    const int64_t n = offsets[scan + 1] - p0;
+    const int64_t start = (int64_t)blockIdx.x * K1_TILE;
+    if (start >= n) return;
+    const int64_t cells = (int64_t)cfg.R * cfg.S;
+    uint32_t *grid = keys + (int64_t)scan_local * cells;
+    const int64_t remain = n - start;
+    const int in_tile = remain < K1_TILE ? (int)remain : K1_TILE;
+    StatAcc acc;
+    if constexpr (STRIDE16) {
+        const uint8_t *base = pts + (p0 + start) * 16;
+        float4 v[K1_PPT];
+#pragma unroll
+        for (int k = 0; k < K1_PPT; ++k) {
+            const int i = k * K1_THREADS + threadIdx.x;
+            if (i < in_tile) v[k] = ld_stream_f4(base + (int64_t)i * 16);
+        }
+#pragma unroll
+        for (int k = 0; k < K1_PPT; ++k) {
+            const int i = k * K1_THREADS + threadIdx.x;
+            if (i < in_tile) accumulate_point<FAST>(cfg, v[k].x, v[k].y, v[k].z, grid, acc);
+        }
+    } else {
+        const uint8_t *base = pts + (p0 + start) * (int64_t)stride_bytes;
+        for (int k = 0; k < K1_PPT; ++k) {
+            const int i = k * K1_THREADS + threadIdx.x;
+            if (i < in_tile) {
+                const uint8_t *q = base + (int64_t)i * stride_bytes;
+                accumulate_point<FAST>(cfg, ld_stream_f1(q), ld_stream_f1(q + 4), ld_stream_f1(q + 8), grid, acc);
+            }
+        }
+    }
+    if (stats) flush_stats(acc, stats + (int64_t)scan * 6, in_tile, threadIdx.x == 0);
+}
+
+// keys -> float grid (coalesced 128-bit), and re-zero the scratch for the next chunk.
+__global__ void __launch_bounds__(256)
+k1_decode(uint32_t *__restrict__ keys, float *__restrict__ out, int64_t n_vec4)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec4; i += stride) {
+        uint4 k = reinterpret_cast<uint4 *>(keys)[i];
+        float4 f;
+        f.x = dsc::key_to_float(k.x);
+        f.y = dsc::key_to_float(k.y);
+        f.z = dsc::key_to_float(k.z);
+        f.w = dsc::key_to_float(k.w);
+        __stcs(reinterpret_cast<float4 *>(out) + i, f);
+        reinterpret_cast<uint4 *>(keys)[i] = make_uint4(0, 0, 0, 0);
+    }
+}
+__global__ void __launch_bounds__(256)
+k1_decode_scalar(uint32_t *__restrict__ keys, float *__restrict__ out, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        out[i] = dsc::key_to_float(keys[i]);
+        keys[i] = 0;
+    }
+}
+
+// ---- K4: to_tensor01 (tiny_sc_ped.py:54-60) ---------------------------------------------------
+__global__ void k4_init_minmax(uint32_t *mm, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mm[2 * i] = 0xffffffffu; mm[2 * i + 1] = 0u; }
+}
+
+// key order that also orders -0 < +0 consistently; NaNs are not expected in grids
+__global__ void __launch_bounds__(256)
+k4_minmax(const float *__restrict__ grids, int64_t cells, uint32_t *__restrict__ mm)
+{
+    const int g = blockIdx.y;
+    const float *p = grids + (int64_t)g * cells;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = dsc::float_to_key(p[i]);
+        lo = min(lo, k);
+        hi = max(hi, k);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    __shared__ uint32_t s_lo[8], s_hi[8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_lo[w] = lo; s_hi[w] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { lo = min(lo, s_lo[i]); hi = max(hi, s_hi[i]); }
+        atomicMin(mm + 2 * g, lo);
+        atomicMax(mm + 2 * g + 1, hi);
+    }
+}
+
+__device__ __forceinline__ float key_to_float_raw(uint32_t k)
+{
+    return dsc::u2f((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256)
+k4_apply(const float *__restrict__ grids, int64_t cells, const uint32_t *__restrict__ mm,
+         float *__restrict__ out)
+{
+    const int g = blockIdx.y;
+    const float mn = key_to_float_raw(mm[2 * g]), mx = key_to_float_raw(mm[2 * g + 1]);
+    const float *p = grids + (int64_t)g * cells;
+    float *o = out + (int64_t)g * cells;
+    const bool scale = mx > mn;
+    // (mx - mn) is a Python-float (f64) subtraction in the reference, then a weak f32 scalar
+    const float d = (float)__dsub_rn((double)mx, (double)mn);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = p[i];
+        o[i] = scale ? __fdiv_rn(__fsub_rn(x, mn), d) : x;
+    }
+}
+
+}  // namespace
+
+// ---- host side ----------------------------------------------------------------------------------
+
+int dsc_check_launch(dsc_ctx *ctx, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return DSC_ERR_CUDA;
+    }
+    ctx->launches++;
+    return DSC_OK;
+}
+
+static int validate_params(dsc_ctx *ctx, const dsc_params *p)
+{
+    if (!p) DSC_FAIL(ctx, DSC_ERR_INVALID, "params is NULL");
+    if (p->num_ring <= 0 || p->num_sector <= 0) DSC_FAIL(ctx, DSC_ERR_INVALID, "num_ring/num_sector must be > 0");
+    if ((int64_t)p->num_ring * p->num_sector > (int64_t)1 << 26)
+        DSC_FAIL(ctx, DSC_ERR_INVALID, "num_ring*num_sector too large");
+    if (!(p->max_length > 0.0) || !isfinite(p->max_length)) DSC_FAIL(ctx, DSC_ERR_INVALID, "max_length must be finite and > 0");
+    if (p->variant != DSC_VARIANT_A && p->variant != DSC_VARIANT_B) DSC_FAIL(ctx, DSC_ERR_INVALID, "unknown variant");
+    return DSC_OK;
+}
+
+static int normalize_device(dsc_ctx *ctx, const float *grids, int n, int64_t cells, float *out,
+                            cudaStream_t st)
+{
+    if (n <= 0) return DSC_OK;
+    if ((size_t)n > ctx->minmax_cap) {
+        if (ctx->minmax) cudaFree(ctx->minmax);
+        ctx->minmax = nullptr;
+        ctx->minmax_cap = 0;
+        DSC_CUDA(ctx, cudaMalloc(&ctx->minmax, sizeof(uint32_t) * 2 * (size_t)n));
+        ctx->minmax_cap = (size_t)n;
+    }
+    int rc;
+    for (int g0 = 0; g0 < n; g0 += 32768) {
+        const int gn = n - g0 < 32768 ? n - g0 : 32768;
+        uint32_t *mm = ctx->minmax + 2 * (size_t)g0;
+        k4_init_minmax<<<(gn + 255) / 256, 256, 0, st>>>(mm, gn);
+        if ((rc = dsc_check_launch(ctx, "k4_init_minmax"))) return rc;
+        int bx = (int)((cells + 256 * 8 - 1) / (256 * 8));
+        if (bx < 1) bx = 1;
+        if (bx > 64) bx = 64;
+        dim3 grid(bx, gn);
+        k4_minmax<<<grid, 256, 0, st>>>(grids + (int64_t)g0 * cells, cells, mm);
+        if ((rc = dsc_check_launch(ctx, "k4_minmax"))) return rc;
+        k4_apply<<<grid, 256, 0, st>>>(grids + (int64_t)g0 * cells, cells, mm, out + (int64_t)g0 * cells);
+        if ((rc = dsc_check_launch(ctx, "k4_apply"))) return rc;
+    }
+    return DSC_OK;
+}
+
+// Device-resident batch: pts/out/stats are device pointers, offsets already on the device.
+static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, const int64_t *d_offsets,
+                        const int64_t *h_offsets, int n_scans, int stride, float *out, float *out_norm,
+                        dsc_scan_stats *stats, cudaStream_t st)
+{
+    const int64_t cells = (int64_t)p->num_ring * p->num_sector;
+    const BinCfg cfg = dsc::make_bin_cfg(p->num_ring, p->num_sector, p->max_length, p->variant,
+                                         p->full_height, p->height_offset,
+                                         (p->flags & DSC_FLAG_GAP_F32) != 0,
+                                         (p->flags & DSC_FLAG_EXACT_ONLY) != 0);
+    // key scratch: sized to stay L2-resident between build and decode
+    int slots = (int)((size_t)48 * 1024 * 1024 / (size_t)(cells * 4));
+    if (slots < 1) slots = 1;
+    if (slots > 4096) slots = 4096;
+    if (slots > n_scans) slots = n_scans;
+    const size_t need = (size_t)slots * cells * 4;
+    if (need > ctx->keys_bytes) {
+        if (ctx->keys) cudaFree(ctx->keys);
+        ctx->keys = nullptr;
+        ctx->keys_bytes = 0;
+        DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
+        ctx->keys_bytes = need;
+        DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
+    }
+    if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
+    const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
+    int rc;
+    for (int s0 = 0; s0 < n_scans; s0 += slots) {
+        const int g = n_scans - s0 < slots ? n_scans - s0 : slots;
+        int64_t max_n = 0;
+        for (int s = s0; s < s0 + g; ++s) {
+            const int64_t n = h_offsets[s + 1] - h_offsets[s];
+            if (n > max_n) max_n = n;
+        }
+        if (max_n > 0) {
+            const int64_t tiles = (max_n + K1_TILE - 1) / K1_TILE;
+            if (tiles > 0x7fffffff) DSC_FAIL(ctx, DSC_ERR_INVALID, "scan too large");
+            dim3 grid((unsigned)tiles, (unsigned)g);
+            unsigned long long *stp = (unsigned long long *)stats;
+            if (vec16 && cfg.fast_ok)
+                k1_build_keys<true, true><<<grid, K1_THREADS, 0, st>>>(pts, d_offsets, s0, ctx->keys, stp, stride, cfg);
+            else if (vec16)
+                k1_build_keys<true, false><<<grid, K1_THREADS, 0, st>>>(pts, d_offsets, s0, ctx->keys, stp, stride, cfg);
+            else if (cfg.fast_ok)
+                k1_build_keys<false, true><<<grid, K1_THREADS, 0, st>>>(pts, d_offsets, s0, ctx->keys, stp, stride, cfg);
+            else
+                k1_build_keys<false, false><<<grid, K1_THREADS, 0, st>>>(pts, d_offsets, s0, ctx->keys, stp, stride, cfg);
+            if ((rc = dsc_check_launch(ctx, "k1_build_keys"))) return rc;
+        }
+        const int64_t total = (int64_t)g * cells;
+        float *o = out + (int64_t)s0 * cells;
+        if ((cells & 3) == 0 && (((uintptr_t)o) & 15) == 0) {
+            const int64_t nv = total / 4;
+            int blocks = (int)((nv + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (nv + 255) / 256
+                                                                              : (int64_t)ctx->sm_count * 16);
+            k1_decode<<<blocks, 256, 0, st>>>(ctx->keys, o, nv);
+        } else {
+            int blocks = (int)((total + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (total + 255) / 256
+                                                                                 : (int64_t)ctx->sm_count * 16);
+            k1_decode_scalar<<<blocks, 256, 0, st>>>(ctx->keys, o, total);
+        }
+        if ((rc = dsc_check_launch(ctx, "k1_decode"))) return rc;
+    }
+    if (out_norm) {
+        if ((rc = normalize_device(ctx, out, n_scans, cells, out_norm, st))) return rc;
+    }
+    return DSC_OK;
+}
+
+static int upload_offsets(dsc_ctx *ctx, const int64_t *offsets, int n_scans, cudaStream_t st)
+{
+    const size_t cnt = (size_t)n_scans + 1;
+    if (cnt > ctx->d_offsets_cap) {
+        if (ctx->d_offsets) cudaFree(ctx->d_offsets);
+        if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
+        ctx->d_offsets = nullptr;
+        ctx->h_offsets = nullptr;
+        ctx->d_offsets_cap = ctx->h_offsets_cap = 0;
+        const size_t cap = cnt < 4096 ? 4096 : cnt * 2;
+        DSC_CUDA(ctx, cudaMalloc(&ctx->d_offsets, cap * sizeof(int64_t)));
+        DSC_CUDA(ctx, cudaMallocHost(&ctx->h_offsets, cap * sizeof(int64_t)));
+        ctx->d_offsets_cap = ctx->h_offsets_cap = cap;
+    } else {
+        // the pinned staging buffer may still be in flight from the previous async call
+        DSC_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    memcpy(ctx->h_offsets, offsets, cnt * sizeof(int64_t));
+    DSC_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, ctx->h_offsets, cnt * sizeof(int64_t),
+                                  cudaMemcpyHostToDevice, st));
+    return DSC_OK;
+}
+
+static void free_stage(dsc_ctx *ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage_pts[i]) cudaFree(ctx->stage_pts[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+        if (ctx->stage_norm[i]) cudaFree(ctx->stage_norm[i]);
+        if (ctx->stage_stats[i]) cudaFree(ctx->stage_stats[i]);
+        if (ctx->stage_doff[i]) cudaFree(ctx->stage_doff[i]);
+        if (ctx->stage_hoff[i]) cudaFreeHost(ctx->stage_hoff[i]);
+        ctx->stage_pts[i] = nullptr;
+        ctx->stage_out[i] = nullptr;
+        ctx->stage_norm[i] = nullptr;
+        ctx->stage_stats[i] = nullptr;
+        ctx->stage_doff[i] = nullptr;
+        ctx->stage_hoff[i] = nullptr;
+    }
+    ctx->stage_pts_cap = 0;
+    ctx->stage_scans_cap = 0;
+    ctx->stage_cells = 0;
+}
+
+void dsc_k1_release(dsc_ctx *ctx)
+{
+    free_stage(ctx);
+    if (ctx->keys) cudaFree(ctx->keys);
+    if (ctx->d_offsets) cudaFree(ctx->d_offsets);
+    if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
+    if (ctx->minmax) cudaFree(ctx->minmax);
+    ctx->keys = nullptr;
+    ctx->d_offsets = nullptr;
+    ctx->h_offsets = nullptr;
+    ctx->minmax = nullptr;
+}
+
+// Host-resident batch: chunked, double-buffered pipeline over three streams
+//   s_h2d: points of chunk i+1 go up   |  s_k: kernels of chunk i  |  s_d2h: grids of chunk i-1 come down
+// so the PCIe link runs in both directions while the SMs work.
+static int build_host(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, const int64_t *offsets,
+                      int n_scans, int stride, float *out, float *out_norm, dsc_scan_stats *stats)
+{
+    const int64_t cells = (int64_t)p->num_ring * p->num_sector;
+    const size_t chunk_bytes_target = (size_t)64 << 20;
+    size_t max_scan_bytes = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        const size_t b = (size_t)(offsets[s + 1] - offsets[s]) * stride;
+        if (b > max_scan_bytes) max_scan_bytes = b;
+    }
+    const size_t pts_cap = max_scan_bytes > chunk_bytes_target ? max_scan_bytes : chunk_bytes_target;
+    const size_t scans_cap = 128;
+    if (pts_cap > ctx->stage_pts_cap || scans_cap > ctx->stage_scans_cap || (size_t)cells != ctx->stage_cells) {
+        DSC_CUDA(ctx, cudaDeviceSynchronize());
+        free_stage(ctx);
+        for (int i = 0; i < 2; ++i) {
+            DSC_CUDA(ctx, cudaMalloc(&ctx->stage_pts[i], pts_cap + 16));
+            DSC_CUDA(ctx, cudaMalloc(&ctx->stage_out[i], scans_cap * cells * 4));
+            DSC_CUDA(ctx, cudaMalloc(&ctx->stage_norm[i], scans_cap * cells * 4));
+            DSC_CUDA(ctx, cudaMalloc(&ctx->stage_stats[i], scans_cap * sizeof(dsc_scan_stats)));
+            DSC_CUDA(ctx, cudaMalloc(&ctx->stage_doff[i], (scans_cap + 1) * sizeof(int64_t)));
+            DSC_CUDA(ctx, cudaMallocHost(&ctx->stage_hoff[i], (scans_cap + 1) * sizeof(int64_t)));
+        }
+        ctx->stage_pts_cap = pts_cap;
+        ctx->stage_scans_cap = scans_cap;
+        ctx->stage_cells = (size_t)cells;
+    }
+    int s0 = 0, buf = 0, rc = DSC_OK;
+    int used[2] = {0, 0};
+    while (s0 < n_scans) {
+        int s1 = s0;
+        size_t bytes = 0;
+        while (s1 < n_scans && (size_t)(s1 - s0) < scans_cap) {
+            const size_t b = (size_t)(offsets[s1 + 1] - offsets[s1]) * stride;
+            if (s1 > s0 && bytes + b > pts_cap) break;
+            bytes += b;
+            ++s1;
+        }
+        const int g = s1 - s0;
+        if (used[buf]) {
+            // pinned offsets of this buffer are rewritten below: its previous upload must be done;
+            // the previous kernels reading stage_pts[buf] must be done before we overwrite it
+            DSC_CUDA(ctx, cudaEventSynchronize(ctx->ev_h2d[buf]));
+            DSC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[buf], 0));
+        }
+        int64_t *ho = ctx->stage_hoff[buf];
+        for (int s = 0; s <= g; ++s) ho[s] = offsets[s0 + s] - offsets[s0];
+        DSC_CUDA(ctx, cudaMemcpyAsync(ctx->stage_doff[buf], ho, (size_t)(g + 1) * sizeof(int64_t),
+                                      cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (bytes)
+            DSC_CUDA(ctx, cudaMemcpyAsync(ctx->stage_pts[buf], pts + (size_t)offsets[s0] * stride, bytes,
+                                          cudaMemcpyHostToDevice, ctx->s_h2d));
+        DSC_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[buf], ctx->s_h2d));
+        DSC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_h2d[buf], 0));
+        if (used[buf]) DSC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_k, ctx->ev_d2h[buf], 0));
+        if ((rc = build_device(ctx, p, (const uint8_t *)ctx->stage_pts[buf], ctx->stage_doff[buf], ho, g, stride,
+                               ctx->stage_out[buf], out_norm ? ctx->stage_norm[buf] : nullptr,
+                               stats ? ctx->stage_stats[buf] : nullptr, ctx->s_k)))
+            return rc;
+        DSC_CUDA(ctx, cudaEventRecord(ctx->ev_k[buf], ctx->s_k));
+        DSC_CUDA(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[buf], 0));
+        DSC_CUDA(ctx, cudaMemcpyAsync(out + (int64_t)s0 * cells, ctx->stage_out[buf], (size_t)g * cells * 4,
+                                      cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (out_norm)
+            DSC_CUDA(ctx, cudaMemcpyAsync(out_norm + (int64_t)s0 * cells, ctx->stage_norm[buf],
+                                          (size_t)g * cells * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (stats)
+            DSC_CUDA(ctx, cudaMemcpyAsync(stats + s0, ctx->stage_stats[buf], (size_t)g * sizeof(dsc_scan_stats),
+                                          cudaMemcpyDeviceToHost, ctx->s_d2h));
+        DSC_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[buf], ctx->s_d2h));
+        used[buf] = 1;
+        s0 = s1;
+        buf ^= 1;
+    }
+    DSC_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    DSC_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));
+    DSC_CUDA(ctx, cudaStreamSynchronize(ctx->s_h2d));
+    return DSC_OK;
+}
+
+extern "C" int dsc_sc_build_batch(dsc_ctx *ctx, const dsc_params *params, const void *pts,
+                                  const int64_t *offsets, int n_scans, int pts_stride_bytes, int mem,
+                                  float *out_grids, float *out_norm, dsc_scan_stats *stats, void *stream)
+{
+    if (!ctx) return DSC_ERR_INVALID;
+    int rc;
+    if ((rc = validate_params(ctx, params))) return rc;
+    if (n_scans < 0) DSC_FAIL(ctx, DSC_ERR_INVALID, "n_scans < 0");
+    if (n_scans == 0) return DSC_OK;
+    if (!offsets || !out_grids) DSC_FAIL(ctx, DSC_ERR_INVALID, "offsets/out_grids is NULL");
+    if (pts_stride_bytes != 16 && pts_stride_bytes != 12) DSC_FAIL(ctx, DSC_ERR_INVALID, "pts_stride_bytes must be 12 or 16");
+    if (mem != DSC_MEM_HOST && mem != DSC_MEM_DEVICE) DSC_FAIL(ctx, DSC_ERR_INVALID, "bad mem");
+    for (int s = 0; s < n_scans; ++s)
+        if (offsets[s + 1] < offsets[s] || offsets[s] < 0) DSC_FAIL(ctx, DSC_ERR_INVALID, "offsets must be non-decreasing and >= 0");
+    if (offsets[n_scans] > offsets[0] && !pts) DSC_FAIL(ctx, DSC_ERR_INVALID, "pts is NULL");
+    DSC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (mem == DSC_MEM_HOST) {
+        return build_host(ctx, params, (const uint8_t *)pts, offsets, n_scans, pts_stride_bytes, out_grids,
+                          out_norm, stats);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = upload_offsets(ctx, offsets, n_scans, st))) return rc;
+    if (ctx->timing) DSC_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    rc = build_device(ctx, params, (const uint8_t *)pts, ctx->d_offsets, offsets, n_scans, pts_stride_bytes,
+                      out_grids, out_norm, stats, st);
+    if (rc) return rc;
+    if (ctx->timing) {
+        DSC_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+        DSC_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        DSC_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    }
+    return DSC_OK;
+}
+
+extern "C" int dsc_sc_normalize01(dsc_ctx *ctx, const float *grids, int n_grids, int64_t cells_per_grid,
+                                  int mem, float *out, void *stream)
+{
+    if (!ctx) return DSC_ERR_INVALID;
+    if (n_grids < 0 || cells_per_grid <= 0) DSC_FAIL(ctx, DSC_ERR_INVALID, "bad sizes");
+    if (n_grids == 0) return DSC_OK;
+    if (!grids || !out) DSC_FAIL(ctx, DSC_ERR_INVALID, "NULL buffer");
+    DSC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (mem == DSC_MEM_DEVICE) return normalize_device(ctx, grids, n_grids, cells_per_grid, out, (cudaStream_t)stream);
+    const size_t bytes = (size_t)n_grids * cells_per_grid * 4;
+    int rc;
+    if ((rc = dsc_reserve_scratch(ctx, bytes * 2))) return rc;
+    float *d_in = (float *)ctx->scratch, *d_out = d_in + (size_t)n_grids * cells_per_grid;
+    cudaStream_t st = ctx->s_k;
+    DSC_CUDA(ctx, cudaMemcpyAsync(d_in, grids, bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = normalize_device(ctx, d_in, n_grids, cells_per_grid, d_out, st))) return rc;
+    DSC_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    DSC_CUDA(ctx, cudaStreamSynchronize(st));
+    return DSC_OK;
+}

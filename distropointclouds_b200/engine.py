@@ -1,0 +1,315 @@
+"""Python front-end of the C-ABI engine: one ``Engine`` per GPU.
+
+Host arrays are NumPy; device arrays are torch CUDA tensors (torch is only the allocator and
+stream provider here -- every kernel that runs is in libdsc.so).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+
+
+@dataclass(frozen=True)
+class ScanContextParams:
+    """The statics the reference keeps on its classes (scaner_version2.py:28-47,
+    kitti_dataset.py:28-41, reconstruct_pointcloud.py:32-45, scan_context_node.py:31-45)."""
+    num_ring: int = 160
+    num_sector: int = 720
+    max_length: float = 20.0
+    variant: int = _ffi.VARIANT_A
+    full_height: bool = True
+    height_offset: float = 2.0
+    gap_f32: bool = False       # variant A called with Python-int resolutions
+    exact_only: bool = False    # disable the screened fast path
+
+    def c(self) -> _ffi.DscParams:
+        flags = (_ffi.FLAG_GAP_F32 if self.gap_f32 else 0) | (_ffi.FLAG_EXACT_ONLY if self.exact_only else 0)
+        return _ffi.DscParams(int(self.num_ring), int(self.num_sector), float(self.max_length),
+                              int(self.variant), int(bool(self.full_height)), float(self.height_offset), flags)
+
+    @property
+    def cells(self) -> int:
+        return int(self.num_ring) * int(self.num_sector)
+
+
+def polar_tables(num_ring: int, num_sector: int, max_length: float):
+    """Cell-centre tables built with NumPy exactly as the reference builds them
+    (kitti_dataset.py:219-229; reconstruct_pointcloud.py:52-59)."""
+    gap_ring = max_length / num_ring
+    gap_sector = 360.0 / num_sector
+    r_centers = (np.arange(num_ring) + 0.5) * gap_ring
+    theta = np.deg2rad((np.arange(num_sector) + 0.5) * gap_sector)
+    return (np.ascontiguousarray(r_centers, dtype=np.float64),
+            np.ascontiguousarray(np.cos(theta), dtype=np.float64),
+            np.ascontiguousarray(np.sin(theta), dtype=np.float64))
+
+
+def _ptr(a) -> Optional[int]:
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())      # torch tensor
+
+
+def pack_scans(scans: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray, int]:
+    """Concatenate per-scan (N,3|4) float32 arrays into one packed buffer.
+    Returns (buffer, offsets int64[n+1], stride_bytes).  The reference's ``scan[:, :-1]`` view of
+    an (N,4) file buffer is passed through without a copy when there is a single scan."""
+    if len(scans) == 0:
+        return np.zeros((0, 4), np.float32), np.zeros(1, np.int64), 16
+    cols = {int(s.shape[1]) for s in scans}
+    for s in scans:
+        if s.dtype != np.float32:
+            raise TypeError("scan-context engine takes float32 points (the .bin dtype); got %s" % s.dtype)
+        if s.ndim != 2 or s.shape[1] not in (3, 4):
+            raise ValueError("points must be (N,3) or (N,4)")
+    offsets = np.zeros(len(scans) + 1, np.int64)
+    np.cumsum([s.shape[0] for s in scans], out=offsets[1:])
+    if len(scans) == 1:
+        s = scans[0]
+        if s.shape[0] == 0:
+            return np.zeros((0, 4), np.float32), offsets, 16
+        if s.flags.c_contiguous:
+            return s, offsets, 4 * s.shape[1]
+        if s.shape[1] == 3 and s.strides == (16, 4):
+            # strided xyz view of packed xyzi rows: hand the rows over as they lie in memory.
+            # The last row's padding float may lie outside the view, so only do it when the
+            # base buffer really owns 4 floats per row.
+            base = s.base
+            if isinstance(base, np.ndarray) and base.dtype == np.float32 and base.flags.c_contiguous \
+                    and base.size >= 4 * s.shape[0] and base.ctypes.data == s.ctypes.data:
+                return base.reshape(-1)[: 4 * s.shape[0]].reshape(-1, 4), offsets, 16
+    stride_cols = 4 if cols == {4} else 3
+    buf = np.empty((int(offsets[-1]), stride_cols), np.float32)
+    for s, a, b in zip(scans, offsets[:-1], offsets[1:]):
+        buf[a:b] = s[:, :stride_cols]
+    return buf, offsets, 4 * stride_cols
+
+
+class Engine:
+    """Owns one dsc_ctx (one GPU).  Not thread-safe; must not be used from forked children."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _ffi.load()
+        h = C.c_void_p()
+        rc = self._lib.dsc_create(int(device), C.byref(h))
+        if rc != _ffi.DSC_OK:
+            raise _ffi.DscError(rc, "dsc_create failed (no CUDA device? the engine has no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        self._tables_key = None
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dsc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int, allow=()):
+        if rc != _ffi.DSC_OK and rc not in allow:
+            raise _ffi.DscError(rc, self._lib.dsc_last_error(self._h).decode())
+        return rc
+
+    @property
+    def version(self) -> str:
+        return self._lib.dsc_version().decode()
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.dsc_kernel_launches(self._h))
+
+    def set_timing(self, enabled: bool):
+        self._check(self._lib.dsc_set_timing(self._h, int(enabled)))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.dsc_last_kernel_ms(self._h))
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """NumPy array over page-locked host memory (freed with the engine)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self._lib.dsc_host_alloc(self._h, n, C.byref(p)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return arr
+
+    # -- K1 ------------------------------------------------------------------------------------
+    def build_host(self, pts: np.ndarray, offsets: np.ndarray, params: ScanContextParams,
+                   stride_bytes: Optional[int] = None, want_norm: bool = False, want_stats: bool = True,
+                   out: Optional[np.ndarray] = None, out_norm: Optional[np.ndarray] = None):
+        """Host buffers in, host buffers out (H2D/D2H inside).  Returns (grids, norm|None, stats|None)."""
+        pts = np.asarray(pts)
+        if pts.dtype != np.float32 or not pts.flags.c_contiguous:
+            raise TypeError("pts must be a C-contiguous float32 array")
+        if stride_bytes is None:
+            stride_bytes = 4 * pts.shape[1]
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        if out is None:
+            out = np.empty((n, params.num_ring, params.num_sector), np.float32)
+        if want_norm and out_norm is None:
+            out_norm = np.empty_like(out)
+        stats = np.zeros((n, len(_ffi.STATS_FIELDS)), np.int64) if want_stats else None
+        cp = params.c()
+        self._check(self._lib.dsc_sc_build_batch(self._h, C.byref(cp), _ptr(pts), _ptr(offsets), n,
+                                                 int(stride_bytes), _ffi.MEM_HOST, _ptr(out),
+                                                 _ptr(out_norm) if want_norm else None, _ptr(stats), None))
+        return out, (out_norm if want_norm else None), stats
+
+    def build_device(self, pts, offsets: np.ndarray, params: ScanContextParams, out, out_norm=None,
+                     stats=None, stride_bytes: int = 16, stream: Optional[int] = None):
+        """Device-resident batch.  ``pts``/``out``/``out_norm``/``stats`` are torch CUDA tensors
+        (stats: int64 [n,6]); ``offsets`` is a host int64 array.  Stream-ordered, asynchronous."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        cp = params.c()
+        self._check(self._lib.dsc_sc_build_batch(self._h, C.byref(cp), _ptr(pts), _ptr(offsets), n,
+                                                 int(stride_bytes), _ffi.MEM_DEVICE, _ptr(out), _ptr(out_norm),
+                                                 _ptr(stats), C.c_void_p(stream)))
+
+    def build_scans(self, scans: Sequence[np.ndarray], params: ScanContextParams, want_norm=False):
+        pts, offsets, stride = pack_scans(scans)
+        return self.build_host(pts, offsets, params, stride_bytes=stride, want_norm=want_norm)
+
+    # -- K4 ------------------------------------------------------------------------------------
+    def normalize01_host(self, grids: np.ndarray) -> np.ndarray:
+        g = np.ascontiguousarray(grids, dtype=np.float32)
+        g3 = g.reshape((-1,) + g.shape[-2:]) if g.ndim >= 2 else g.reshape(1, -1)
+        out = np.empty_like(g3)
+        cells = int(np.prod(g3.shape[1:]))
+        self._check(self._lib.dsc_sc_normalize01(self._h, _ptr(g3), g3.shape[0], cells, _ffi.MEM_HOST,
+                                                 _ptr(out), None))
+        return out.reshape(g.shape)
+
+    def normalize01_device(self, grids, out, stream: Optional[int] = None):
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        n = int(grids.shape[0])
+        cells = int(grids.numel() // max(n, 1))
+        self._check(self._lib.dsc_sc_normalize01(self._h, _ptr(grids), n, cells, _ffi.MEM_DEVICE, _ptr(out),
+                                                 C.c_void_p(stream)))
+
+    # -- tables --------------------------------------------------------------------------------
+    def set_tables(self, num_ring: int, num_sector: int, max_length: float):
+        key = (int(num_ring), int(num_sector), float(max_length))
+        if key == self._tables_key:
+            return
+        rc_, ct, st = polar_tables(*key)
+        self._check(self._lib.dsc_set_polar_tables(self._h, key[0], key[1], _ptr(rc_), _ptr(ct), _ptr(st)))
+        self._tables_key = key
+
+    # -- K2 ------------------------------------------------------------------------------------
+    def raster_boxes_host(self, boxes_xylwyaw: np.ndarray, num_ring=160, num_sector=720, max_length=20.0,
+                          want_mask: bool = False):
+        """boxes: (B,5) float64 x,y,l,w,yaw.  Returns (list of (K,2) int64 arrays, mask|None)."""
+        self.set_tables(num_ring, num_sector, max_length)
+        b = np.asarray(boxes_xylwyaw, dtype=np.float64).reshape(-1, 5)
+        nb = b.shape[0]
+        packed = np.empty((nb, 6), np.float64)
+        packed[:, :4] = b[:, :4]
+        packed[:, 4] = np.cos(b[:, 4])      # kitti_dataset.py:236
+        packed[:, 5] = np.sin(b[:, 4])      # kitti_dataset.py:237
+        offs = np.zeros(nb + 1, np.int64)
+        mask = np.zeros((num_ring, num_sector), np.uint8) if want_mask else None
+        cap = max(1024, 256 * nb)
+        while True:
+            cells = np.empty((cap, 2), np.int32)
+            rc = self._lib.dsc_raster_boxes(self._h, _ptr(packed), nb, _ffi.MEM_HOST, _ptr(offs), _ptr(cells),
+                                            cap, _ptr(mask), None)
+            if rc == _ffi.DSC_ERR_CAPACITY:
+                cap = int(offs[nb])
+                continue
+            self._check(rc)
+            break
+        out = [cells[offs[i]:offs[i + 1]].astype(np.int64) for i in range(nb)]
+        return out, mask
+
+    # -- K3 ------------------------------------------------------------------------------------
+    def reconstruct_host(self, grids: np.ndarray, num_ring=160, num_sector=720, max_length=20.0,
+                         full_height=True, height_offset=2.0):
+        """grids (n,R,S) or (R,S) float32.  Returns list of (points (K,3) f64, bin_ids (K,) int32)."""
+        self.set_tables(num_ring, num_sector, max_length)
+        g = np.ascontiguousarray(grids, dtype=np.float32).reshape(-1, num_ring, num_sector)
+        n = g.shape[0]
+        offs = np.zeros(n + 1, np.int64)
+        cap = int(np.count_nonzero(g)) if full_height else int(np.count_nonzero(g > 0))
+        pts = np.empty((max(cap, 1), 3), np.float64)
+        ids = np.empty((max(cap, 1),), np.int32)
+        self._check(self._lib.dsc_reconstruct_batch(self._h, _ptr(g), n, int(bool(full_height)),
+                                                    float(height_offset), _ffi.MEM_HOST, _ptr(offs), _ptr(pts),
+                                                    _ptr(ids), cap, None))
+        return [(pts[offs[i]:offs[i + 1]].copy(), ids[offs[i]:offs[i + 1]].copy()) for i in range(n)]
+
+    def reconstruct_device(self, grids, pt_offsets, pts_out, bin_ids_out, num_ring=160, num_sector=720,
+                           max_length=20.0, full_height=True, height_offset=2.0, stream: Optional[int] = None):
+        """All torch CUDA tensors; capacity is pts_out.shape[0]; pt_offsets int64 [n+1] on device."""
+        self.set_tables(num_ring, num_sector, max_length)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        n = int(grids.shape[0])
+        self._check(self._lib.dsc_reconstruct_batch(self._h, _ptr(grids), n, int(bool(full_height)),
+                                                    float(height_offset), _ffi.MEM_DEVICE, _ptr(pt_offsets),
+                                                    _ptr(pts_out), _ptr(bin_ids_out), int(pts_out.shape[0]),
+                                                    C.c_void_p(stream)))
+
+    # -- K5 ------------------------------------------------------------------------------------
+    def covered_mask_host(self, bin_ids: np.ndarray, cells: np.ndarray, num_ring=160, num_sector=720,
+                          max_length=20.0) -> np.ndarray:
+        self.set_tables(num_ring, num_sector, max_length)
+        ids = np.ascontiguousarray(bin_ids, dtype=np.int32)
+        c = np.ascontiguousarray(np.asarray(cells).reshape(-1, 2), dtype=np.int32)
+        mask = np.zeros(ids.shape[0], np.uint8)
+        self._check(self._lib.dsc_covered_mask(self._h, _ptr(ids), ids.shape[0], _ptr(c), c.shape[0],
+                                               _ffi.MEM_HOST, _ptr(mask), None))
+        return mask.astype(bool)
+
+    def gather_cells_host(self, grid: np.ndarray, cells: np.ndarray, num_ring=160, num_sector=720,
+                          max_length=20.0) -> np.ndarray:
+        self.set_tables(num_ring, num_sector, max_length)
+        g = np.ascontiguousarray(grid, dtype=np.float32)
+        c = np.ascontiguousarray(np.asarray(cells).reshape(-1, 2), dtype=np.int32)
+        pts = np.empty((c.shape[0], 3), np.float64)
+        self._check(self._lib.dsc_gather_cells(self._h, _ptr(g), _ptr(c), c.shape[0], _ffi.MEM_HOST, _ptr(pts),
+                                               None))
+        return pts
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device, created on first use."""
+    with _default_lock:
+        e = _default.get(device)
+        if e is None:
+            e = _default[device] = Engine(device)
+        return e

@@ -1,0 +1,42 @@
+// host_math.cpp -- compiles distropointclouds_b200/csrc/dsc_math.cuh as plain C++ (g++,
+// -ffp-contract=off) so the per-point binning code the CUDA kernels run can be checked against
+// the oracle on a machine without a GPU.  TEST INFRASTRUCTURE: not part of libdsc.so.
+#include "../distropointclouds_b200/csrc/dsc_math.cuh"
+
+extern "C" {
+
+float hm_atan2f(float y, float x) { return dsc::atan2f_fdlibm(y, x); }
+
+// status/cell/z per point through the exact path
+void hm_bin_exact(int R, int S, double max_length, int variant, int full_height, float offset, int gap_f32,
+                  const float *xyz, long long n, int stride_floats, int *cell, int *status, float *z)
+{
+    const dsc::BinCfg c = dsc::make_bin_cfg(R, S, max_length, variant, full_height, offset, gap_f32, 1);
+    for (long long i = 0; i < n; ++i) {
+        const float *p = xyz + i * stride_floats;
+        const dsc::BinResult b = dsc::bin_exact(c, p[0], p[1], p[2]);
+        cell[i] = b.cell; status[i] = b.status; z[i] = b.z;
+    }
+}
+
+#ifdef DSC_HAVE_FAST
+// screened fast path with an emulated MUFU error model: `noise` holds per-point relative
+// perturbations (in units of 2^-22) applied to the approximate reciprocal / rsqrt.
+void hm_bin_fast(int R, int S, double max_length, int variant, int full_height, float offset,
+                 const float *xyz, long long n, int stride_floats, const float *noise, int *cell, int *status,
+                 int *took_slow)
+{
+    const dsc::BinCfg c = dsc::make_bin_cfg(R, S, max_length, variant, full_height, offset, 0, 0);
+    for (long long i = 0; i < n; ++i) {
+        const float *p = xyz + i * stride_floats;
+        bool slow = false;
+        const dsc::BinResult b = dsc::bin_screened(c, p[0], p[1], p[2], noise ? noise[2 * i] : 0.f,
+                                                   noise ? noise[2 * i + 1] : 0.f, &slow);
+        cell[i] = b.cell; status[i] = b.status; took_slow[i] = slow;
+    }
+}
+#endif
+
+unsigned hm_float_to_key(float z) { return dsc::float_to_key(z); }
+float hm_key_to_float(unsigned k) { return dsc::key_to_float(k); }
+}

@@ -1,0 +1,95 @@
+"""Host-side logic: packing, sharding, and the world_size-2 gather over gloo (CPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from distropointclouds_b200.engine import ScanContextParams, pack_scans, polar_tables
+from distropointclouds_b200.sharding import shard_bounds
+
+
+def test_pack_scans_passes_file_view_through_without_copy(tmp_path):
+    raw = np.arange(40, dtype=np.float32)
+    f = tmp_path / "x.bin"
+    raw.tofile(f)
+    scan = np.fromfile(f, dtype=np.float32).reshape((-1, 4))
+    view = scan[:, :-1]                                  # what load_velo_scan returns
+    buf, offs, stride = pack_scans([view])
+    assert stride == 16 and buf.shape == (10, 4) and buf.ctypes.data == view.ctypes.data
+    assert list(offs) == [0, 10]
+
+
+def test_pack_scans_ragged_and_empty():
+    a = np.ones((5, 4), np.float32); b = np.zeros((0, 4), np.float32); c = 2 * np.ones((3, 4), np.float32)
+    buf, offs, stride = pack_scans([a, b, c])
+    assert stride == 16 and list(offs) == [0, 5, 5, 8] and buf.shape == (8, 4)
+    buf, offs, stride = pack_scans([a[:, :3], c[:, :3]])
+    assert stride == 12 and buf.shape == (8, 3)
+    with pytest.raises(TypeError):
+        pack_scans([a.astype(np.float64)])
+    buf, offs, stride = pack_scans([])
+    assert list(offs) == [0]
+
+
+def test_params_struct():
+    p = ScanContextParams(gap_f32=True, exact_only=True).c()
+    assert p.flags == 3 and p.num_ring == 160 and p.max_length == 20.0
+
+
+def test_polar_tables_are_the_reference_expressions():
+    rc, ct, st = polar_tables(160, 720, 20.0)
+    assert rc[0] == 0.0625 and rc[-1] == 19.9375 and ct.shape == (720,)
+    th = np.deg2rad((np.arange(720) + 0.5) * 0.5)
+    assert np.array_equal(ct, np.cos(th)) and np.array_equal(st, np.sin(th))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_shard_bounds_cover_and_balance(world):
+    rng = np.random.default_rng(world)
+    counts = rng.integers(0, 200000, 37)
+    b = shard_bounds(counts, world)
+    assert b[0][0] == 0 and b[-1][1] == 37 and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+    loads = [counts[a:e].sum() for a, e in b]
+    if world <= 8:
+        assert max(loads) <= counts.sum() / world + counts.max()
+    assert shard_bounds([5, 5], 4)[-1][1] == 2            # more ranks than scans
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as orc
+    from distropointclouds_b200.sharding import gather_grids, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    scans = [(rng.standard_normal((n, 4)) * 8).astype(np.float32) for n in (900, 300, 1200, 50, 700)]
+    counts = [len(s) for s in scans]
+    bounds = shard_bounds(counts, world)
+    a, e = bounds[rank]
+    # the oracle stands in for the GPU engine here: this test covers the sharding + gather logic only
+    local = np.stack([orc.sc_build(s)[0] for s in scans[a:e]]) if e > a else np.zeros((0, 160, 720), np.float32)
+    full = gather_grids(torch.from_numpy(local), len(scans), bounds).numpy()
+    ref = np.stack([orc.sc_build(s)[0] for s in scans])
+    q.put((rank, bool(np.array_equal(full, ref))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_gather_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
