@@ -18,7 +18,7 @@ FLAG_GAP_F32, FLAG_EXACT_ONLY = 1, 2
 
 EXPORTS = (
     "dsc_version", "dsc_create", "dsc_destroy", "dsc_last_error", "dsc_set_timing", "dsc_last_kernel_ms",
-    "dsc_kernel_launches", "dsc_host_alloc", "dsc_host_free", "dsc_sc_build_batch", "dsc_sc_normalize01",
+    "dsc_kernel_launches", "dsc_set_option", "dsc_host_alloc", "dsc_host_free", "dsc_sc_build_batch", "dsc_sc_normalize01",
     "dsc_set_polar_tables", "dsc_raster_boxes", "dsc_reconstruct_batch", "dsc_covered_mask",
     "dsc_gather_cells",
 )
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     L.dsc_set_timing.argtypes = [vp, ip]
     L.dsc_last_kernel_ms.argtypes = [vp]
     L.dsc_last_kernel_ms.restype = C.c_float
+    L.dsc_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.dsc_kernel_launches.argtypes = [vp]
     L.dsc_kernel_launches.restype = C.c_int64
     L.dsc_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]

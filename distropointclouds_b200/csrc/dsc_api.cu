@@ -1,5 +1,6 @@
 // dsc_api.cu -- context lifetime and small entry points of the C ABI (include/dsc.h).
 #include "dsc_internal.h"
+#include <stdlib.h>
 
 void dsc_k1_release(dsc_ctx *ctx);
 
@@ -23,6 +24,7 @@ extern "C" int dsc_create(int device, dsc_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = prop.l2CacheSize;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (const char *e = getenv("DSC_K1_IMPL")) ctx->k1_impl = atoi(e);   // debugging / A-B benchmarking only
     bool ok = cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess &&
@@ -67,6 +69,12 @@ extern "C" int dsc_set_timing(dsc_ctx *ctx, int enabled)
     ctx->timing = enabled != 0;
     ctx->last_ms = -1.0f;
     return DSC_OK;
+}
+extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name) return DSC_ERR_INVALID;
+    if (!strcmp(name, "k1_impl") && value >= 0 && value <= 2) { ctx->k1_impl = (int)value; return DSC_OK; }
+    DSC_FAIL(ctx, DSC_ERR_INVALID, std::string("unknown option or bad value: ") + name);
 }
 extern "C" float dsc_last_kernel_ms(const dsc_ctx *ctx) { return ctx ? ctx->last_ms : -1.0f; }
 extern "C" int64_t dsc_kernel_launches(const dsc_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -135,6 +135,121 @@ k1_build_keys(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offse
     if (stats) flush_stats(acc, stats + (int64_t)scan * 6, in_tile, threadIdx.x == 0);
 }
 
+
+// ---- K1 main path: shared-memory-resident half grids -----------------------------------------------
+// The 160x720 float32 grid (460 800 B) does not fit one SM's shared memory, DSMEM atomics are ~15x
+// slower than local ones on B200 (profiles/microbench: 77 vs 1120 Gop/s) and L2 atomics ~6x slower.
+// So a scan is owned by a PAIR of CTAs that split the grid by sector: CTA `half` keeps the keys of
+// sectors [half*S/2, (half+1)*S/2) for all rings in shared memory (160*360*4 = 230 400 B).  Both CTAs
+// stream all points of the scan (the second read hits L2, HBM sees each point once) and a point is
+// claimed by the CTA whose half contains its sector.  Because S/2 sectors are exactly 180 degrees,
+// "which half" is sign(y) except within a hair of the seam; both CTAs evaluate seam points and the
+// computed sector decides.  There is no traffic between the CTAs at all: reduction = local ATOMS.MAX,
+// write-out = one coalesced pass per scan that also re-zeroes the grid for the next scan.
+constexpr int HG_THREADS = 1024;
+constexpr int HG_U = 4;                         // 128-bit loads in flight per thread (64 KB per SM)
+constexpr int HG_STEP = HG_THREADS * HG_U;
+
+template <bool FAST>
+__device__ __forceinline__ void hg_point(const BinCfg &cfg, const float4 v, uint32_t *sgrid, int half, int Sh,
+                                         StatAcc &acc)
+{
+    float xs = v.x, ys = v.y;
+    if (cfg.variant == 0) {                     // claim on the substituted coordinates (scaner_version2.py:85-86)
+        if (xs == 0.0f) xs = 0.001f;
+        if (ys == 0.0f) ys = 0.001f;
+    }
+    const float c = 0.001953125f * fabsf(xs);   // seam band: |angle to the 0/180 axis| < 0.11 deg
+    // written so that NaNs are claimed by both CTAs (every comparison is false)
+    const bool claim0 = !(ys < -c), claim1 = !(ys > c);
+    if (!(half == 0 ? claim0 : claim1)) return;
+    BinResult b;
+    bool slow = false;
+    if constexpr (FAST) {
+        b = dsc::bin_screened(cfg, v.x, v.y, v.z, 0.0f, 0.0f, &slow);
+        if (slow) b = dsc::bin_exact(cfg, v.x, v.y, v.z);
+    } else {
+        b = dsc::bin_exact(cfg, v.x, v.y, v.z);
+    }
+    if (b.status > dsc::PT_CLAMPED) {           // dropped points have no sector: counted exactly once,
+        if (half == 0 || !claim0) {             // by half 0 when it claims the point, else by half 1
+            acc.nonfinite += (b.status == dsc::PT_NONFINITE);
+            acc.overflow += (b.status == dsc::PT_SECTOR_OVERFLOW);
+            acc.oor += (b.status == dsc::PT_OUT_OF_RANGE);
+            acc.slow += slow;
+        }
+        return;
+    }
+    const int local = b.sector - half * Sh;
+    if ((unsigned)local >= (unsigned)Sh) return;   // seam point that belongs to the partner
+    acc.clamped += (b.status == dsc::PT_CLAMPED);
+    acc.slow += slow;
+    const float zv = b.z;
+    if (zv != zv) return;
+    if (!cfg.full_height && !(zv > 0.0f)) return;
+    const uint32_t key = dsc::float_to_key(zv);
+    uint32_t *cell = sgrid + b.ring * Sh + local;
+    if (key > *cell) atomicMax(cell, key);      // LDS pre-check: most points are not a new maximum
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(HG_THREADS, 1)
+k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
+            float *__restrict__ out, unsigned long long *__restrict__ stats, BinCfg cfg)
+{
+    extern __shared__ __align__(16) uint32_t sgrid[];
+    const int Sh = cfg.S >> 1;
+    const int half = blockIdx.x & 1;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int nvec = (cfg.R * Sh) >> 2;         // host guarantees Sh % 4 == 0
+    const int rowvec = Sh >> 2;
+    for (int i = threadIdx.x; i < nvec; i += HG_THREADS) reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int scan = pair; scan < n_scans; scan += npairs) {
+        const int64_t p0 = offsets[scan];
+        const int64_t n = offsets[scan + 1] - p0;
+        const uint8_t *src = pts + p0 * 16;
+        StatAcc acc;
+        float4 cur[HG_U], nxt[HG_U];
+#pragma unroll
+        for (int u = 0; u < HG_U; ++u) {
+            const int64_t i = (int64_t)u * HG_THREADS + threadIdx.x;
+            if (i < n) cur[u] = ld_stream_f4(src + i * 16);
+        }
+        for (int64_t base = 0; base < n; base += HG_STEP) {
+            const int64_t nb = base + HG_STEP;
+#pragma unroll
+            for (int u = 0; u < HG_U; ++u) {    // prefetch the next step while this one is binned
+                const int64_t i = nb + (int64_t)u * HG_THREADS + threadIdx.x;
+                if (i < n) nxt[u] = ld_stream_f4(src + i * 16);
+            }
+#pragma unroll
+            for (int u = 0; u < HG_U; ++u) {
+                const int64_t i = base + (int64_t)u * HG_THREADS + threadIdx.x;
+                if (i < n) hg_point<FAST>(cfg, cur[u], sgrid, half, Sh, acc);
+            }
+#pragma unroll
+            for (int u = 0; u < HG_U; ++u) cur[u] = nxt[u];
+        }
+        __syncthreads();
+        // one coalesced write-out of this CTA's half of every ring row, re-zeroing the keys on the way
+        float *o = out + (int64_t)scan * cfg.R * cfg.S + half * Sh;
+        for (int i = threadIdx.x; i < nvec; i += HG_THREADS) {
+            const int r = i / rowvec, j4 = i - r * rowvec;
+            const uint4 k = reinterpret_cast<uint4 *>(sgrid)[i];
+            reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
+            float4 f;
+            f.x = dsc::key_to_float(k.x);
+            f.y = dsc::key_to_float(k.y);
+            f.z = dsc::key_to_float(k.z);
+            f.w = dsc::key_to_float(k.w);
+            __stcs(reinterpret_cast<float4 *>(o + (int64_t)r * cfg.S) + j4, f);
+        }
+        if (stats) flush_stats(acc, stats + (int64_t)scan * 6, n, half == 0 && threadIdx.x == 0);
+        __syncthreads();
+    }
+}
+
 // keys -> float grid (coalesced 128-bit), and re-zero the scratch for the next chunk.
 __global__ void __launch_bounds__(256)
 k1_decode(uint32_t *__restrict__ keys, float *__restrict__ out, int64_t n_vec4)
@@ -282,6 +397,30 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
                                          p->full_height, p->height_offset,
                                          (p->flags & DSC_FLAG_GAP_F32) != 0,
                                          (p->flags & DSC_FLAG_EXACT_ONLY) != 0);
+    const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
+    int rc;
+    if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
+    // ---- main path: shared-memory half grids, one CTA pair per scan, persistent over the batch ----
+    const size_t hg_smem = (size_t)cells * 2;   // R * S/2 * 4 bytes
+    const bool hg_ok = vec16 && (p->num_sector % 8) == 0 && hg_smem <= ctx->smem_optin &&
+                       (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1 &&
+                       (ctx->k1_impl == 2 || n_scans >= ctx->sm_count / 8);
+    if (hg_ok) {
+        int pairs = ctx->sm_count / 2;
+        if (pairs > n_scans) pairs = n_scans;
+        unsigned long long *stp = (unsigned long long *)stats;
+        if (cfg.fast_ok) {
+            DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));
+            k1_halfgrid<true><<<2 * pairs, HG_THREADS, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp, cfg);
+        } else {
+            DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));
+            k1_halfgrid<false><<<2 * pairs, HG_THREADS, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp, cfg);
+        }
+        if ((rc = dsc_check_launch(ctx, "k1_halfgrid"))) return rc;
+        if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
+        return DSC_OK;
+    }
+    // ---- fallback path (small batches, odd grids, 12-byte stride): key grid in L2 + RED.MAX ----
     // key scratch: sized to stay L2-resident between build and decode
     int slots = (int)((size_t)48 * 1024 * 1024 / (size_t)(cells * 4));
     if (slots < 1) slots = 1;
@@ -296,9 +435,6 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         ctx->keys_bytes = need;
         DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
     }
-    if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
-    const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
-    int rc;
     for (int s0 = 0; s0 < n_scans; s0 += slots) {
         const int g = n_scans - s0 < slots ? n_scans - s0 : slots;
         int64_t max_n = 0;

@@ -224,6 +224,7 @@ static inline BinCfg make_bin_cfg(int R, int S, double max_length, int variant, 
 
 struct BinResult {
     int32_t cell;    // ring * S + sector, valid when status <= PT_CLAMPED
+    int32_t ring, sector;
     int32_t status;
     float   z;       // height after the mode's offset
 };
@@ -234,7 +235,7 @@ struct BinResult {
 DSC_HD BinResult bin_exact_a(const BinCfg &c, float x, float y, float z)
 {
     BinResult o;
-    o.cell = 0;
+    o.cell = 0; o.ring = 0; o.sector = 0;
     o.z = c.full_height ? z : fadd(z, c.offset);   // :73-82, float32 add
     if (x == 0.0f) x = 0.001f;                     // :85-86
     if (y == 0.0f) y = 0.001f;
@@ -271,6 +272,8 @@ DSC_HD BinResult bin_exact_a(const BinCfg &c, float x, float y, float z)
         o.status = PT_SECTOR_OVERFLOW;
         return o;
     }
+    o.ring = ring;
+    o.sector = sector;
     o.cell = ring * c.S + sector;
     o.status = clamped ? PT_CLAMPED : PT_OK;
     return o;
@@ -280,7 +283,7 @@ DSC_HD BinResult bin_exact_a(const BinCfg &c, float x, float y, float z)
 DSC_HD BinResult bin_exact_b(const BinCfg &c, float x, float y, float z)
 {
     BinResult o;
-    o.cell = 0;
+    o.cell = 0; o.ring = 0; o.sector = 0;
     o.z = z;
     if (!(fabsf(x) < INFINITY) || !(fabsf(y) < INFINITY) || !(fabsf(z) < INFINITY)) {  // :115-117
         o.status = PT_NONFINITE;
@@ -300,6 +303,8 @@ DSC_HD BinResult bin_exact_b(const BinCfg &c, float x, float y, float z)
     const float sf = floorf(fdiv(t, c.gap_sector_f));       // :144
     const int ring = rf > (float)(c.R - 1) ? c.R - 1 : (rf < 0.0f ? 0 : (int)rf);     // :143
     const int sector = sf > (float)(c.S - 1) ? c.S - 1 : (sf < 0.0f ? 0 : (int)sf);   // :145
+    o.ring = ring;
+    o.sector = sector;
     o.cell = ring * c.S + sector;
     o.status = PT_OK;
     return o;
@@ -355,7 +360,7 @@ DSC_HD BinResult bin_screened(const BinCfg &c, float x, float y, float z, float 
                               bool *slow)
 {
     BinResult o;
-    o.cell = 0;
+    o.cell = 0; o.ring = 0; o.sector = 0;
     o.status = PT_OK;
     o.z = c.full_height ? z : fadd(z, c.offset);
     if (c.variant == 0) {
@@ -399,7 +404,9 @@ DSC_HD BinResult bin_screened(const BinCfg &c, float x, float y, float z, float 
         return o;
     }
     const int ring = beyond ? c.R - 1 : min_i((int)fr, c.R - 1);
-    o.cell = ring * c.S + (int)fs;
+    o.ring = ring;
+    o.sector = (int)fs;
+    o.cell = ring * c.S + o.sector;
     return o;
 }
 

@@ -137,6 +137,9 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.dsc_kernel_launches(self._h))
 
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.dsc_set_option(self._h, name.encode(), int(value)))
+
     def set_timing(self, enabled: bool):
         self._check(self._lib.dsc_set_timing(self._h, int(enabled)))
 

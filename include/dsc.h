@@ -88,6 +88,9 @@ const char *dsc_last_error(const dsc_ctx *ctx);
  * (dsc_set_timing(ctx,1)); the call then synchronises the stream.  -1 if not available. */
 int dsc_set_timing(dsc_ctx *ctx, int enabled);
 float dsc_last_kernel_ms(const dsc_ctx *ctx);
+/* Engine options (debugging / A-B measurements):
+ *   "k1_impl"  0 = auto, 1 = force the L2-key-grid kernel, 2 = force the shared-memory half-grid kernel */
+int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value);
 /* Number of engine kernels launched since the context was created. */
 int64_t dsc_kernel_launches(const dsc_ctx *ctx);
 
