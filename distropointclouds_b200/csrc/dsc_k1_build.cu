@@ -146,16 +146,13 @@ k1_build_keys(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offse
 // "which half" is sign(y) except within a hair of the seam; both CTAs evaluate seam points and the
 // computed sector decides.  There is no traffic between the CTAs at all: reduction = local ATOMS.MAX,
 // write-out = one coalesced pass per scan that also re-zeroes the grid for the next scan.
-constexpr int HG_THREADS = 1024;
-constexpr int HG_U = 4;                         // 128-bit loads in flight per thread (64 KB per SM)
-constexpr int HG_STEP = HG_THREADS * HG_U;
 
-template <bool FAST>
-__device__ __forceinline__ void hg_point(const BinCfg &cfg, const float4 v, uint32_t *sgrid, int half, int Sh,
-                                         StatAcc &acc)
+template <bool FAST, int VARIANT, bool FULL>
+__device__ __forceinline__ void hg_point(const BinCfg &cfg_in, const float4 v, uint32_t *sgrid, const int half,
+                                         const int Sh, StatAcc &acc)
 {
     float xs = v.x, ys = v.y;
-    if (cfg.variant == 0) {                     // claim on the substituted coordinates (scaner_version2.py:85-86)
+    if (VARIANT == 0) {                         // claim on the substituted coordinates (scaner_version2.py:85-86)
         if (xs == 0.0f) xs = 0.001f;
         if (ys == 0.0f) ys = 0.001f;
     }
@@ -163,6 +160,9 @@ __device__ __forceinline__ void hg_point(const BinCfg &cfg, const float4 v, uint
     // written so that NaNs are claimed by both CTAs (every comparison is false)
     const bool claim0 = !(ys < -c), claim1 = !(ys > c);
     if (!(half == 0 ? claim0 : claim1)) return;
+    BinCfg cfg = cfg_in;                        // let the compiler fold the mode switches away
+    cfg.variant = VARIANT;
+    cfg.full_height = FULL;
     BinResult b;
     bool slow = false;
     if constexpr (FAST) {
@@ -186,56 +186,67 @@ __device__ __forceinline__ void hg_point(const BinCfg &cfg, const float4 v, uint
     acc.slow += slow;
     const float zv = b.z;
     if (zv != zv) return;
-    if (!cfg.full_height && !(zv > 0.0f)) return;
+    if (!FULL && !(zv > 0.0f)) return;
     const uint32_t key = dsc::float_to_key(zv);
     uint32_t *cell = sgrid + b.ring * Sh + local;
     if (key > *cell) atomicMax(cell, key);      // LDS pre-check: most points are not a new maximum
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(HG_THREADS, 1)
+template <bool FAST, int VARIANT, bool FULL, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 1)
 k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
-            float *__restrict__ out, unsigned long long *__restrict__ stats, BinCfg cfg)
+            float *__restrict__ out, unsigned long long *__restrict__ stats, const BinCfg cfg)
 {
+    constexpr int STEP = THREADS * U;           // points per step: U 128-bit loads in flight per thread and set
     extern __shared__ __align__(16) uint32_t sgrid[];
+    const int tid = threadIdx.x;
     const int Sh = cfg.S >> 1;
     const int half = blockIdx.x & 1;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int nvec = (cfg.R * Sh) >> 2;         // host guarantees Sh % 4 == 0
     const int rowvec = Sh >> 2;
-    for (int i = threadIdx.x; i < nvec; i += HG_THREADS) reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
+    const int dr = THREADS / rowvec, dj = THREADS - dr * rowvec;   // row/column advance per THREADS vec4
+    for (int i = tid; i < nvec; i += THREADS) reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     for (int scan = pair; scan < n_scans; scan += npairs) {
         const int64_t p0 = offsets[scan];
-        const int64_t n = offsets[scan + 1] - p0;
-        const uint8_t *src = pts + p0 * 16;
+        const int n = (int)(offsets[scan + 1] - p0);          // host guarantees < 2^31 points per scan
+        const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         StatAcc acc;
-        float4 cur[HG_U], nxt[HG_U];
+        // ---- stream the scan: two register sets ping-pong, U x 128-bit loads in flight per set ----
+        const int nfull = n / STEP;
+        const float4 *p = s4 + tid;
+        float4 a[U], b[U];
+        if (nfull > 0) {
 #pragma unroll
-        for (int u = 0; u < HG_U; ++u) {
-            const int64_t i = (int64_t)u * HG_THREADS + threadIdx.x;
-            if (i < n) cur[u] = ld_stream_f4(src + i * 16);
+            for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
         }
-        for (int64_t base = 0; base < n; base += HG_STEP) {
-            const int64_t nb = base + HG_STEP;
+        int step = 0;
+        while (step + 1 < nfull) {
 #pragma unroll
-            for (int u = 0; u < HG_U; ++u) {    // prefetch the next step while this one is binned
-                const int64_t i = nb + (int64_t)u * HG_THREADS + threadIdx.x;
-                if (i < n) nxt[u] = ld_stream_f4(src + i * 16);
+            for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * THREADS);
+#pragma unroll
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, a[u], sgrid, half, Sh, acc);
+            p += 2 * STEP;
+            step += 2;
+            if (step < nfull) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
             }
 #pragma unroll
-            for (int u = 0; u < HG_U; ++u) {
-                const int64_t i = base + (int64_t)u * HG_THREADS + threadIdx.x;
-                if (i < n) hg_point<FAST>(cfg, cur[u], sgrid, half, Sh, acc);
-            }
-#pragma unroll
-            for (int u = 0; u < HG_U; ++u) cur[u] = nxt[u];
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, b[u], sgrid, half, Sh, acc);
         }
+        if (step < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, a[u], sgrid, half, Sh, acc);
+        }
+        for (int i = nfull * STEP + tid; i < n; i += THREADS)              // ragged tail
+            hg_point<FAST, VARIANT, FULL>(cfg, ld_stream_f4(s4 + i), sgrid, half, Sh, acc);
         __syncthreads();
-        // one coalesced write-out of this CTA's half of every ring row, re-zeroing the keys on the way
+        // ---- one coalesced write-out of this CTA's half of every ring row, re-zeroing the keys ----
         float *o = out + (int64_t)scan * cfg.R * cfg.S + half * Sh;
-        for (int i = threadIdx.x; i < nvec; i += HG_THREADS) {
-            const int r = i / rowvec, j4 = i - r * rowvec;
+        int r = tid / rowvec, j4 = tid - r * rowvec;
+        for (int i = tid; i < nvec; i += THREADS) {
             const uint4 k = reinterpret_cast<uint4 *>(sgrid)[i];
             reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
             float4 f;
@@ -243,9 +254,12 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
             f.y = dsc::key_to_float(k.y);
             f.z = dsc::key_to_float(k.z);
             f.w = dsc::key_to_float(k.w);
-            __stcs(reinterpret_cast<float4 *>(o + (int64_t)r * cfg.S) + j4, f);
+            __stcs(reinterpret_cast<float4 *>(o + r * cfg.S) + j4, f);
+            r += dr;
+            j4 += dj;
+            if (j4 >= rowvec) { j4 -= rowvec; ++r; }
         }
-        if (stats) flush_stats(acc, stats + (int64_t)scan * 6, n, half == 0 && threadIdx.x == 0);
+        if (stats) flush_stats(acc, stats + (int64_t)scan * 6, n, half == 0 && tid == 0);
         __syncthreads();
     }
 }
@@ -409,13 +423,28 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         int pairs = ctx->sm_count / 2;
         if (pairs > n_scans) pairs = n_scans;
         unsigned long long *stp = (unsigned long long *)stats;
+#define HG_LAUNCH2(F, V, H, T, U)                                                                               \
+    do {                                                                                                        \
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<F, V, H, T, U>,                                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));         \
+        k1_halfgrid<F, V, H, T, U><<<2 * pairs, T, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp, cfg);      \
+    } while (0)
+#define HG_LAUNCH(F, V, H)                                                                                      \
+    do {                                                                                                        \
+        if (ctx->hg_cfg == 1) HG_LAUNCH2(F, V, H, 1024, 2);                                                     \
+        else if (ctx->hg_cfg == 2) HG_LAUNCH2(F, V, H, 512, 2);                                                 \
+        else HG_LAUNCH2(F, V, H, 512, 4);                                                                       \
+    } while (0)
+        const bool full = p->full_height != 0;
         if (cfg.fast_ok) {
-            DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));
-            k1_halfgrid<true><<<2 * pairs, HG_THREADS, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp, cfg);
+            if (p->variant == 0) { if (full) HG_LAUNCH(true, 0, true); else HG_LAUNCH(true, 0, false); }
+            else                 { if (full) HG_LAUNCH(true, 1, true); else HG_LAUNCH(true, 1, false); }
         } else {
-            DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));
-            k1_halfgrid<false><<<2 * pairs, HG_THREADS, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp, cfg);
+            if (p->variant == 0) { if (full) HG_LAUNCH(false, 0, true); else HG_LAUNCH(false, 0, false); }
+            else                 { if (full) HG_LAUNCH(false, 1, true); else HG_LAUNCH(false, 1, false); }
         }
+#undef HG_LAUNCH
+#undef HG_LAUNCH2
         if ((rc = dsc_check_launch(ctx, "k1_halfgrid"))) return rc;
         if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
         return DSC_OK;
@@ -629,8 +658,10 @@ extern "C" int dsc_sc_build_batch(dsc_ctx *ctx, const dsc_params *params, const 
     if (!offsets || !out_grids) DSC_FAIL(ctx, DSC_ERR_INVALID, "offsets/out_grids is NULL");
     if (pts_stride_bytes != 16 && pts_stride_bytes != 12) DSC_FAIL(ctx, DSC_ERR_INVALID, "pts_stride_bytes must be 12 or 16");
     if (mem != DSC_MEM_HOST && mem != DSC_MEM_DEVICE) DSC_FAIL(ctx, DSC_ERR_INVALID, "bad mem");
-    for (int s = 0; s < n_scans; ++s)
+    for (int s = 0; s < n_scans; ++s) {
         if (offsets[s + 1] < offsets[s] || offsets[s] < 0) DSC_FAIL(ctx, DSC_ERR_INVALID, "offsets must be non-decreasing and >= 0");
+        if (offsets[s + 1] - offsets[s] > 0x7fff0000LL) DSC_FAIL(ctx, DSC_ERR_INVALID, "more than 2^31 points in one scan");
+    }
     if (offsets[n_scans] > offsets[0] && !pts) DSC_FAIL(ctx, DSC_ERR_INVALID, "pts is NULL");
     DSC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (mem == DSC_MEM_HOST) {
