@@ -147,64 +147,130 @@ k1_build_keys(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offse
 // computed sector decides.  There is no traffic between the CTAs at all: reduction = local ATOMS.MAX,
 // write-out = one coalesced pass per scan that also re-zeroes the grid for the next scan.
 
-template <bool FAST, int VARIANT, bool FULL>
-__device__ __forceinline__ void hg_point(const BinCfg &cfg_in, const float4 v, uint32_t *sgrid, const int half,
-                                         const int Sh, StatAcc &acc)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    float xs = v.x, ys = v.y;
-    if (VARIANT == 0) {                         // claim on the substituted coordinates (scaner_version2.py:85-86)
-        if (xs == 0.0f) xs = 0.001f;
-        if (ys == 0.0f) ys = 0.001f;
-    }
-    const float c = 0.001953125f * fabsf(xs);   // seam band: |angle to the 0/180 axis| < 0.11 deg
-    // written so that NaNs are claimed by both CTAs (every comparison is false)
-    const bool claim0 = !(ys < -c), claim1 = !(ys > c);
-    if (!(half == 0 ? claim0 : claim1)) return;
-    BinCfg cfg = cfg_in;                        // let the compiler fold the mode switches away
-    cfg.variant = VARIANT;
-    cfg.full_height = FULL;
-    BinResult b;
-    bool slow = false;
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void reds_max_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// The fdlibm chain is ~150 instructions and runs for < 1 % of the points: keep it out of line so the
+// streaming loop stays small (instruction cache) and its registers do not count against the hot path.
+// Everything crosses the call boundary by value (a BinCfg reference would force the caller's copy of
+// the configuration into local memory); the result is packed: x = status << 27 | cell, y = bits of z.
+struct ExactArgs {
+    int R, S, pow2, gap_f32;
+    float inv_gap_ring_f, inv_gap_sector_f, gap_ring_f, gap_sector_f, max_length_f, offset;
+    double gap_ring_d, gap_sector_d;
+};
+template <int VARIANT, bool FULL>
+__device__ __noinline__ uint2 hg_bin_exact(float x, float y, float z, const ExactArgs a)
+{
+    BinCfg c;
+    c.R = a.R; c.S = a.S; c.variant = VARIANT; c.full_height = FULL; c.offset = a.offset;
+    c.pow2 = a.pow2; c.gap_f32 = a.gap_f32;
+    c.inv_gap_ring_f = a.inv_gap_ring_f; c.inv_gap_sector_f = a.inv_gap_sector_f;
+    c.gap_ring_f = a.gap_ring_f; c.gap_sector_f = a.gap_sector_f;
+    c.gap_ring_d = a.gap_ring_d; c.gap_sector_d = a.gap_sector_d;
+    c.max_length_f = a.max_length_f;
+    const BinResult b = dsc::bin_exact(c, x, y, z);
+    return make_uint2(((uint32_t)b.status << 27) | (uint32_t)b.cell, __float_as_uint(b.z));
+}
+
+struct HgConst {
+    uint32_t sgrid;      // shared-window address of the key grid
+    int Sh;              // sectors per half
+    int sector0;         // first sector of this CTA's half
+    float sgn;           // +1 for half 0 (y > 0 side), -1 for half 1
+    int half;
+};
+
+template <bool FAST, int VARIANT, bool FULL>
+__device__ __forceinline__ void hg_point(const BinCfg &cfg, const HgConst &k, const float4 v, StatAcc &acc)
+{
+    // ---- whose point is it?  S/2 sectors are exactly 180 degrees, so it is sign(y) except within a
+    // hair of the seam, where both CTAs evaluate the point and the computed sector decides.  Variant A
+    // substitutes y == 0 by +0.001 (scaner_version2.py:86).  NaNs compare false => claimed by both.
+    float ys = v.y;
+    if (VARIANT == 0 && ys == 0.0f) ys = 0.001f;
+    const float c = fabsf(v.x) * 0.001953125f;   // seam band: |angle to the 0/180 axis| < 0.11 deg
+    if (ys * k.sgn < -c) return;
+    int ring, sector;
+    bool beyond, ok = false;
     if constexpr (FAST) {
-        b = dsc::bin_screened(cfg, v.x, v.y, v.z, 0.0f, 0.0f, &slow);
-        if (slow) b = dsc::bin_exact(cfg, v.x, v.y, v.z);
-    } else {
-        b = dsc::bin_exact(cfg, v.x, v.y, v.z);
+        ok = dsc::screened_core(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
+        if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
     }
-    if (b.status > dsc::PT_CLAMPED) {           // dropped points have no sector: counted exactly once,
-        if (half == 0 || !claim0) {             // by half 0 when it claims the point, else by half 1
-            acc.nonfinite += (b.status == dsc::PT_NONFINITE);
-            acc.overflow += (b.status == dsc::PT_SECTOR_OVERFLOW);
-            acc.oor += (b.status == dsc::PT_OUT_OF_RANGE);
-            acc.slow += slow;
+    float zv = FULL ? v.z : __fadd_rn(v.z, cfg.offset);
+    bool dropped = false;
+    int drop_status = 0;
+    if (!ok) {                                   // near a bin boundary, zero / non-finite coordinate, ...
+        ExactArgs ea;
+        ea.R = cfg.R; ea.S = cfg.S; ea.pow2 = cfg.pow2; ea.gap_f32 = cfg.gap_f32;
+        ea.inv_gap_ring_f = cfg.inv_gap_ring_f; ea.inv_gap_sector_f = cfg.inv_gap_sector_f;
+        ea.gap_ring_f = cfg.gap_ring_f; ea.gap_sector_f = cfg.gap_sector_f;
+        ea.max_length_f = cfg.max_length_f; ea.offset = cfg.offset;
+        ea.gap_ring_d = cfg.gap_ring_d; ea.gap_sector_d = cfg.gap_sector_d;
+        const uint2 b = hg_bin_exact<VARIANT, FULL>(v.x, v.y, v.z, ea);
+        const int status = (int)(b.x >> 27), cell = (int)(b.x & 0x7ffffffu);
+        ring = cell / cfg.S;
+        sector = cell - ring * cfg.S;
+        zv = __uint_as_float(b.y);
+        beyond = status == dsc::PT_CLAMPED;
+        dropped = status > dsc::PT_CLAMPED;
+        drop_status = status;
+        if (FAST) acc.slow++;
+    } else if (VARIANT == 1 && beyond) {
+        dropped = true;
+        drop_status = dsc::PT_OUT_OF_RANGE;
+    }
+    if (dropped) {                               // no sector: count once -- by half 0 if it claims the point
+        const bool claim0 = !(ys < -c);
+        if (k.half == 0 || !claim0) {
+            acc.nonfinite += (drop_status == dsc::PT_NONFINITE);
+            acc.overflow += (drop_status == dsc::PT_SECTOR_OVERFLOW);
+            acc.oor += (drop_status == dsc::PT_OUT_OF_RANGE);
+        } else if (FAST && !ok) {
+            acc.slow--;                          // the partner accounts for this point
         }
         return;
     }
-    const int local = b.sector - half * Sh;
-    if ((unsigned)local >= (unsigned)Sh) return;   // seam point that belongs to the partner
-    acc.clamped += (b.status == dsc::PT_CLAMPED);
-    acc.slow += slow;
-    const float zv = b.z;
-    if (zv != zv) return;
-    if (!FULL && !(zv > 0.0f)) return;
-    const uint32_t key = dsc::float_to_key(zv);
-    uint32_t *cell = sgrid + b.ring * Sh + local;
-    if (key > *cell) atomicMax(cell, key);      // LDS pre-check: most points are not a new maximum
+    const unsigned local = (unsigned)(sector - k.sector0);
+    if (local >= (unsigned)k.Sh) {               // seam point that belongs to the partner
+        if (FAST && !ok) acc.slow--;
+        return;
+    }
+    if (VARIANT == 0 && beyond) acc.clamped++;
+    const uint32_t u = __float_as_uint(zv);
+    uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
+    if (zv != zv) key = 0;                       // NaN never wins (scaner_version2.py:107)
+    if (!FULL && !(zv > 0.0f)) key = 0;          // offset mode: cells start at 0, strict '>'
+    const uint32_t addr = k.sgrid + (uint32_t)(ring * k.Sh + (int)local) * 4u;
+    if (key > lds_u32(addr)) reds_max_u32(addr, key);   // LDS pre-check: most points are not a new maximum
 }
 
 template <bool FAST, int VARIANT, bool FULL, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS, 1)
 k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
-            float *__restrict__ out, unsigned long long *__restrict__ stats, const BinCfg cfg)
+            float *__restrict__ out, unsigned long long *__restrict__ stats, const BinCfg cfg_in)
 {
-    constexpr int STEP = THREADS * U;           // points per step: U 128-bit loads in flight per thread and set
+    constexpr int STEP = THREADS * U;           // points per step: U 128-bit loads in flight per thread
     extern __shared__ __align__(16) uint32_t sgrid[];
+    const BinCfg &cfg = cfg_in;                 // stays in the constant bank: its address is never taken
     const int tid = threadIdx.x;
-    const int Sh = cfg.S >> 1;
-    const int half = blockIdx.x & 1;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int nvec = (cfg.R * Sh) >> 2;         // host guarantees Sh % 4 == 0
-    const int rowvec = Sh >> 2;
+    HgConst k;
+    k.half = blockIdx.x & 1;
+    k.Sh = cfg.S >> 1;
+    k.sector0 = k.half * k.Sh;
+    k.sgn = k.half ? -1.0f : 1.0f;
+    k.sgrid = (uint32_t)__cvta_generic_to_shared(sgrid);
+    const int nvec = (cfg.R * k.Sh) >> 2;       // host guarantees Sh % 4 == 0
+    const int rowvec = k.Sh >> 2;
     const int dr = THREADS / rowvec, dj = THREADS - dr * rowvec;   // row/column advance per THREADS vec4
     for (int i = tid; i < nvec; i += THREADS) reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -213,53 +279,48 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
         const int n = (int)(offsets[scan + 1] - p0);          // host guarantees < 2^31 points per scan
         const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         StatAcc acc;
-        // ---- stream the scan: two register sets ping-pong, U x 128-bit loads in flight per set ----
+        // ---- stream the scan.  Rolling prefetch: each register is re-loaded for the next step as soon
+        // as its point has been handed to the binning code, so U 128-bit loads per thread stay in flight.
         const int nfull = n / STEP;
         const float4 *p = s4 + tid;
-        float4 a[U], b[U];
+        float4 a[U];
         if (nfull > 0) {
 #pragma unroll
             for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
         }
-        int step = 0;
-        while (step + 1 < nfull) {
+        for (int step = 1; step < nfull; ++step) {
+            p += STEP;
 #pragma unroll
-            for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * THREADS);
-#pragma unroll
-            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, a[u], sgrid, half, Sh, acc);
-            p += 2 * STEP;
-            step += 2;
-            if (step < nfull) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
+            for (int u = 0; u < U; ++u) {
+                const float4 v = a[u];
+                a[u] = ld_stream_f4(p + u * THREADS);
+                hg_point<FAST, VARIANT, FULL>(cfg, k, v, acc);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, b[u], sgrid, half, Sh, acc);
         }
-        if (step < nfull) {
+        if (nfull > 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, a[u], sgrid, half, Sh, acc);
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, a[u], acc);
         }
         for (int i = nfull * STEP + tid; i < n; i += THREADS)              // ragged tail
-            hg_point<FAST, VARIANT, FULL>(cfg, ld_stream_f4(s4 + i), sgrid, half, Sh, acc);
+            hg_point<FAST, VARIANT, FULL>(cfg, k, ld_stream_f4(s4 + i), acc);
         __syncthreads();
         // ---- one coalesced write-out of this CTA's half of every ring row, re-zeroing the keys ----
-        float *o = out + (int64_t)scan * cfg.R * cfg.S + half * Sh;
+        float *o = out + (int64_t)scan * cfg.R * cfg.S + k.sector0;
         int r = tid / rowvec, j4 = tid - r * rowvec;
         for (int i = tid; i < nvec; i += THREADS) {
-            const uint4 k = reinterpret_cast<uint4 *>(sgrid)[i];
+            const uint4 q = reinterpret_cast<uint4 *>(sgrid)[i];
             reinterpret_cast<uint4 *>(sgrid)[i] = make_uint4(0, 0, 0, 0);
             float4 f;
-            f.x = dsc::key_to_float(k.x);
-            f.y = dsc::key_to_float(k.y);
-            f.z = dsc::key_to_float(k.z);
-            f.w = dsc::key_to_float(k.w);
+            f.x = dsc::key_to_float(q.x);
+            f.y = dsc::key_to_float(q.y);
+            f.z = dsc::key_to_float(q.z);
+            f.w = dsc::key_to_float(q.w);
             __stcs(reinterpret_cast<float4 *>(o + r * cfg.S) + j4, f);
             r += dr;
             j4 += dj;
             if (j4 >= rowvec) { j4 -= rowvec; ++r; }
         }
-        if (stats) flush_stats(acc, stats + (int64_t)scan * 6, n, half == 0 && tid == 0);
+        if (stats) flush_stats(acc, stats + (int64_t)scan * 6, n, k.half == 0 && tid == 0);
         __syncthreads();
     }
 }
@@ -432,8 +493,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
 #define HG_LAUNCH(F, V, H)                                                                                      \
     do {                                                                                                        \
         if (ctx->hg_cfg == 1) HG_LAUNCH2(F, V, H, 1024, 2);                                                     \
-        else if (ctx->hg_cfg == 2) HG_LAUNCH2(F, V, H, 512, 2);                                                 \
-        else HG_LAUNCH2(F, V, H, 512, 4);                                                                       \
+        else if (ctx->hg_cfg == 2) HG_LAUNCH2(F, V, H, 512, 4);                                                 \
+        else HG_LAUNCH2(F, V, H, 1024, 4);                                                                      \
     } while (0)
         const bool full = p->full_height != 0;
         if (cfg.fast_ok) {

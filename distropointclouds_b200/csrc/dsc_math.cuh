@@ -175,6 +175,7 @@ struct BinCfg {
     int32_t fast_ok;
     float   fast_dr, fast_ds;        // half-widths of the "too close to a boundary" bands (bin units)
     float   q90, q180, q360;         // 90/180/360 degrees in sector units (exact: pow2 scaling)
+    float   Rp1_f;                   // (float)(R + 1)
     float   atan_c[8];               // atan(u)/u minimax in u^2 on [0,1], pre-scaled to sector units
 };
 
@@ -216,6 +217,7 @@ static inline BinCfg make_bin_cfg(int R, int S, double max_length, int variant, 
         c.q90 = (float)(90.0 * inv_s);
         c.q180 = (float)(180.0 * inv_s);
         c.q360 = (float)(360.0 * inv_s);
+        c.Rp1_f = (float)(R + 1);
         c.fast_dr = (float)((R + 1) * 1.5e-6);
         c.fast_ds = (float)(5.0e-4 * inv_s);
     }
@@ -320,7 +322,7 @@ DSC_HD BinResult bin_exact(const BinCfg &c, float x, float y, float z)
 // The exact chain above costs ~100 instructions per point (two IEEE divisions, an IEEE sqrt and 26
 // unfused polynomial steps).  Almost every point sits far from any bin boundary, where a much
 // cheaper approximation provably lands in the same bin.  bin_screened() computes
-//     qr ~ r / gap_ring        (fma + MUFU.RSQ)                          in ring units
+//     qr ~ r / gap_ring        (fma + MUFU.SQRT)                          in ring units
 //     qs ~ theta / gap_sector  (MUFU.RCP + 8-term minimax atan, octant fix-up)  in sector units
 // and accepts the floor() of each only when the value is at least fast_dr / fast_ds away from every
 // integer.  Anything else -- including every NaN/Inf/overflow/underflow, which turn into NaN or land
@@ -332,19 +334,22 @@ DSC_HD BinResult bin_exact(const BinCfg &c, float x, float y, float z)
 //   fast chain vs true      : polynomial 7.4e-6 (measured in f32), rcp.approx+mul 6.9e-6, three
 //                             octant subtractions <= 3e-5                          => < 4.5e-5
 //   sum 9.5e-5 deg; band fast_ds = 5e-4 deg (5x).
-//   ring: rsqrt.approx 2^-22.9 + two multiplies + the fma-vs-unfused difference < 3e-7 relative,
+//   ring: sqrt.approx 2^-23 + one multiply + the fma-vs-unfused difference < 3e-7 relative,
 //   i.e. < (R+1)*3e-7 ring units; band fast_dr = (R+1)*1.5e-6 (5x).
 #if defined(__CUDA_ARCH__)
-DSC_HD float approx_rsqrt(float s, float) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s)); return r; }
+DSC_HD float approx_sqrt(float s, float) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s)); return r; }
 DSC_HD float approx_rcp(float s, float) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s)); return r; }
 DSC_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+DSC_HD float round_nearest(float a) { return rintf(a); }
 #else
 // host emulation for tests/host_math.cpp: correctly rounded value perturbed by `noise` * 2^-22
-// (|noise| <= 1 covers the documented MUFU error), with flush-to-zero of subnormal operands
-DSC_HD float approx_rsqrt(float s, float noise)
+// (|noise| <= 1 covers the documented MUFU error), with flush-to-zero of subnormal operands/results
+DSC_HD float approx_sqrt(float s, float noise)
 {
     if (s == s && fabsf(s) < 1.17549435e-38f) s = copysignf(0.0f, s);
-    return (float)((1.0 / sqrt((double)s)) * (1.0 + (double)noise * 2.384185791015625e-07));
+    float r = (float)(sqrt((double)s) * (1.0 + (double)noise * 2.384185791015625e-07));
+    if (fabsf(r) < 1.17549435e-38f) r = copysignf(0.0f, r);
+    return r;
 }
 DSC_HD float approx_rcp(float s, float noise)
 {
@@ -354,24 +359,21 @@ DSC_HD float approx_rcp(float s, float noise)
     return r;
 }
 DSC_HD float ffma(float a, float b, float c) { return (float)((double)a * (double)b + (double)c); }
+DSC_HD float round_nearest(float a) { return nearbyintf(a); }
 #endif
 
-DSC_HD BinResult bin_screened(const BinCfg &c, float x, float y, float z, float noise_r, float noise_t,
-                              bool *slow)
+// Core of the screen: true when (ring, sector, beyond) are certain; false sends the point to bin_exact.
+// No zero substitution is needed here: a zero coordinate makes u == 0 (or NaN), so the approximate
+// angle is an exact multiple of 90 degrees -- a sector boundary -- and the point screens itself out.
+DSC_HD bool screened_core(const BinCfg &c, float x, float y, float noise_r, float noise_t, int *ring,
+                          int *sector, bool *beyond)
 {
-    BinResult o;
-    o.cell = 0; o.ring = 0; o.sector = 0;
-    o.status = PT_OK;
-    o.z = c.full_height ? z : fadd(z, c.offset);
-    if (c.variant == 0) {
-        if (x == 0.0f) x = 0.001f;
-        if (y == 0.0f) y = 0.001f;
-    }
     const float ax = fabsf(x), ay = fabsf(y);
-    // ring
+    // ring coordinate: sqrt.approx.ftz flushes a subnormal s to 0 (-> boundary 0 -> exact path);
+    // an overflowing s gives +inf, rejected by the explicit finite test
     const float s = ffma(x, x, y * y);
-    const float qr = (s * approx_rsqrt(s, noise_r)) * c.inv_gap_ring_f;
-    // sector
+    const float qr = approx_sqrt(s, noise_r) * c.inv_gap_ring_f;
+    // sector coordinate
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float u = mn * approx_rcp(mx, noise_t);
     const float w = u * u;
@@ -386,27 +388,39 @@ DSC_HD BinResult bin_screened(const BinCfg &c, float x, float y, float z, float 
     if (ay > ax) qs = c.q90 - qs;
     if (x < 0.0f) qs = c.q180 - qs;
     if (y < 0.0f) qs = c.q360 - qs;
-    const float fr = floorf(qr), fs = floorf(qs);
-    // deep in the clamp / reject zone.  qr == +inf only arises from a subnormal s (flushed to 0 by
-    // rsqrt.approx.ftz -> inf, then subnormal * inf): that point is tiny, not far, so it must not pass.
-    const bool far_out = qr >= (float)(c.R + 1) && qr < INFINITY;
-    const bool ring_ok = far_out || (fabsf((qr - fr) - 0.5f) < 0.5f - c.fast_dr);
-    const bool sect_ok = fabsf((qs - fs) - 0.5f) < 0.5f - c.fast_ds;   // NaN compares false
-    bool ok = ring_ok && sect_ok;
+    // distance to the nearest bin boundary (NaN compares false everywhere => not ok)
+    const float dr = fabsf(qr - round_nearest(qr)), ds = fabsf(qs - round_nearest(qs));
+    const bool far_out = qr >= c.Rp1_f;                  // deep in the clamp / reject zone
+    const bool ok = (ds > c.fast_ds) && (far_out || dr > c.fast_dr) && (qr < INFINITY);
+    const int ir = (int)fminf(qr, c.Rp1_f);              // qr >= 0: truncation == floor; clamped so the cast is defined
+    *beyond = ir >= c.R;
+    *ring = min_i(ir, c.R - 1);
+    *sector = (int)qs;
+    return ok;
+}
+
+DSC_HD BinResult bin_screened(const BinCfg &c, float x, float y, float z, float noise_r, float noise_t,
+                              bool *slow)
+{
+    BinResult o;
+    o.cell = 0; o.ring = 0; o.sector = 0;
+    o.status = PT_OK;
+    o.z = c.full_height ? z : fadd(z, c.offset);
+    int ring, sector;
+    bool beyond;
+    bool ok = screened_core(c, x, y, noise_r, noise_t, &ring, &sector, &beyond);
     if (c.variant != 0) ok = ok && (fabsf(z) < INFINITY);              // finite mask (scan_context_node.py:115)
     *slow = !ok;
     if (!ok) return o;
-    const bool beyond = far_out || fr >= (float)c.R;
     if (c.variant == 0) {
         o.status = beyond ? PT_CLAMPED : PT_OK;
     } else if (beyond) {
         o.status = PT_OUT_OF_RANGE;
         return o;
     }
-    const int ring = beyond ? c.R - 1 : min_i((int)fr, c.R - 1);
     o.ring = ring;
-    o.sector = (int)fs;
-    o.cell = ring * c.S + o.sector;
+    o.sector = sector;
+    o.cell = ring * c.S + sector;
     return o;
 }
 
