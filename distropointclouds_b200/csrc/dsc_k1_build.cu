@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
             float *__restrict__ out, unsigned long long *__restrict__ stats, const BinCfg cfg_in)
 {
-    constexpr int STEP = THREADS * U;           // points per step: U 128-bit loads in flight per thread
+    constexpr int STEP = THREADS * U;           // points per step and register set
     extern __shared__ __align__(16) uint32_t sgrid[];
     const BinCfg &cfg = cfg_in;                 // stays in the constant bank: its address is never taken
     const int tid = threadIdx.x;
@@ -279,25 +279,32 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
         const int n = (int)(offsets[scan + 1] - p0);          // host guarantees < 2^31 points per scan
         const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         StatAcc acc;
-        // ---- stream the scan.  Rolling prefetch: each register is re-loaded for the next step as soon
-        // as its point has been handed to the binning code, so U 128-bit loads per thread stay in flight.
+        // ---- stream the scan: two register sets ping-pong, U x 128-bit loads in flight per set.
+        // (A rolling "reload the register right after use" scheme was tried: ptxas copies the freshly
+        // loaded value at once, which serialises on the load -- see profiles/r1_notes.md.)
         const int nfull = n / STEP;
         const float4 *p = s4 + tid;
-        float4 a[U];
+        float4 a[U], b[U];
         if (nfull > 0) {
 #pragma unroll
             for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
         }
-        for (int step = 1; step < nfull; ++step) {
-            p += STEP;
+        int step = 0;
+        while (step + 1 < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float4 v = a[u];
-                a[u] = ld_stream_f4(p + u * THREADS);
-                hg_point<FAST, VARIANT, FULL>(cfg, k, v, acc);
+            for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * THREADS);
+#pragma unroll
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, a[u], acc);
+            p += 2 * STEP;
+            step += 2;
+            if (step < nfull) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, b[u], acc);
         }
-        if (nfull > 0) {
+        if (step < nfull) {
 #pragma unroll
             for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, a[u], acc);
         }
@@ -492,9 +499,9 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     } while (0)
 #define HG_LAUNCH(F, V, H)                                                                                      \
     do {                                                                                                        \
-        if (ctx->hg_cfg == 1) HG_LAUNCH2(F, V, H, 1024, 2);                                                     \
+        if (ctx->hg_cfg == 1) HG_LAUNCH2(F, V, H, 1024, 3);                                                     \
         else if (ctx->hg_cfg == 2) HG_LAUNCH2(F, V, H, 512, 4);                                                 \
-        else HG_LAUNCH2(F, V, H, 1024, 4);                                                                      \
+        else HG_LAUNCH2(F, V, H, 1024, 2);                                                                      \
     } while (0)
         const bool full = p->full_height != 0;
         if (cfg.fast_ok) {
