@@ -148,6 +148,8 @@ def run_ours(args):
     eng = Engine(local_rank)
     eng.set_option("k1_impl", args.k1_impl)
     eng.set_option("hg_cfg", args.hg_cfg)
+    if args.pf_dist >= 0:
+        eng.set_option("pf_dist", args.pf_dist)
     params = ScanContextParams(R, S, MAXLEN)
     B, Pn = args.scans, args.points
 
@@ -263,6 +265,7 @@ def main():
     ap.add_argument("--points", type=int, default=120000, help="points per scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--pf-dist", type=int, default=-1, help="bulk L2 prefetch distance in steps (A/B runs)")
     ap.add_argument("--hg-cfg", type=int, default=0, help="half-grid launch shape (A/B runs)")
     ap.add_argument("--k1-impl", type=int, default=0, help="0 auto, 1 L2-key kernel, 2 half-grid kernel (A/B runs)")
     args = ap.parse_args()

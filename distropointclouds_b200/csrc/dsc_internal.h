@@ -17,6 +17,7 @@ struct dsc_ctx {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
+    int pf_dist = 6;                 // bulk L2 prefetch distance in steps (0 = off)
     int hg_cfg = 0;                  // half-grid launch shape: 0 = 1024 thr x 2 loads x 2 sets, 1 = 1024x3x2, 2 = 512x4x2 (A/B runs)
     int k1_impl = 0;                 // 0 auto, 1 force L2-key kernel, 2 force half-grid kernel (DSC_K1_IMPL)
     float last_ms = -1.0f;

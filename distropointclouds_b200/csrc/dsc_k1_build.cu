@@ -181,6 +181,32 @@ __device__ __noinline__ uint2 hg_bin_exact(float x, float y, float z, const Exac
     return make_uint2(((uint32_t)b.status << 27) | (uint32_t)b.cell, __float_as_uint(b.z));
 }
 
+// Bulk L2 prefetch (UBLKPF.L2, the TMA engine): shared memory is entirely taken by the key grid, so
+// there is no room to stage tiles with cp.async.bulk; instead one thread asks the copy engine to pull
+// the chunk `dist` steps ahead into L2, which turns the 128-bit register loads into L2 hits.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// chunk index counted from the start of `scan`; runs over into this CTA's next scan
+__device__ __forceinline__ void hg_prefetch(const uint8_t *pts, const int64_t *offsets, int scan, int npairs,
+                                            int n_scans, int64_t p0, int n, int chunk, int chunk_bytes)
+{
+    int nch = (int)(((int64_t)n * 16 + chunk_bytes - 1) / chunk_bytes);
+    if (chunk >= nch) {
+        scan += npairs;
+        if (scan >= n_scans) return;
+        chunk -= nch;
+        p0 = offsets[scan];
+        n = (int)(offsets[scan + 1] - p0);
+        nch = (int)(((int64_t)n * 16 + chunk_bytes - 1) / chunk_bytes);
+        if (chunk >= nch) return;
+    }
+    const int64_t off = (int64_t)chunk * chunk_bytes;
+    const int64_t left = (int64_t)n * 16 - off;
+    bulk_prefetch_l2(pts + p0 * 16 + off, (uint32_t)(left < chunk_bytes ? left : chunk_bytes));
+}
+
 struct HgConst {
     uint32_t sgrid;      // shared-window address of the key grid
     int Sh;              // sectors per half
@@ -256,7 +282,8 @@ __device__ __forceinline__ void hg_point(const BinCfg &cfg, const HgConst &k, co
 template <bool FAST, int VARIANT, bool FULL, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS, 1)
 k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
-            float *__restrict__ out, unsigned long long *__restrict__ stats, const BinCfg cfg_in)
+            float *__restrict__ out, unsigned long long *__restrict__ stats, const int pf_dist,
+            const BinCfg cfg_in)
 {
     constexpr int STEP = THREADS * U;           // points per step and register set
     extern __shared__ __align__(16) uint32_t sgrid[];
@@ -279,6 +306,10 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
         const int n = (int)(offsets[scan + 1] - p0);          // host guarantees < 2^31 points per scan
         const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         StatAcc acc;
+        constexpr int CHUNK = STEP * 16;
+        if (pf_dist > 0 && tid == 0 && scan == pair) {       // cold start of this CTA's first scan
+            for (int c = k.half; c < pf_dist; c += 2) hg_prefetch(pts, offsets, scan, npairs, n_scans, p0, n, c, CHUNK);
+        }
         // ---- stream the scan: two register sets ping-pong, U x 128-bit loads in flight per set.
         // (A rolling "reload the register right after use" scheme was tried: ptxas copies the freshly
         // loaded value at once, which serialises on the load -- see profiles/r1_notes.md.)
@@ -291,6 +322,9 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
         }
         int step = 0;
         while (step + 1 < nfull) {
+            // the two CTAs of the pair share the prefetching: even chunks by half 0, odd chunks by half 1
+            if (pf_dist > 0 && tid == 0)
+                hg_prefetch(pts, offsets, scan, npairs, n_scans, p0, n, step + pf_dist + k.half, CHUNK);
 #pragma unroll
             for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * THREADS);
 #pragma unroll
@@ -495,7 +529,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<F, V, H, T, U>,                                          \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));         \
-        k1_halfgrid<F, V, H, T, U><<<2 * pairs, T, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp, cfg);      \
+        k1_halfgrid<F, V, H, T, U><<<2 * pairs, T, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp,        \
+                                                                   ctx->pf_dist, cfg);                          \
     } while (0)
 #define HG_LAUNCH(F, V, H)                                                                                      \
     do {                                                                                                        \
