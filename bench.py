@@ -150,6 +150,8 @@ def run_ours(args):
     eng.set_option("hg_cfg", args.hg_cfg)
     if args.pf_dist >= 0:
         eng.set_option("pf_dist", args.pf_dist)
+    if args.st_slots > 0:
+        eng.set_option("st_slots", args.st_slots)
     params = ScanContextParams(R, S, MAXLEN)
     B, Pn = args.scans, args.points
 
@@ -235,7 +237,7 @@ def run_ours(args):
         }
         if args.skip_e2e:
             line["e2e"] = None
-        line["config"]["k1_impl"] = {0: "auto", 1: "l2keys", 2: "halfgrid"}[args.k1_impl]
+        line["config"]["k1_impl"] = {0: "stream", 1: "l2keys", 2: "halfgrid"}[args.k1_impl]
         if world == 1 and not args.no_cpu_baseline and h_pts is not None:
             from oracle import oracle as orc
             cores = orc.max_threads()
@@ -265,9 +267,10 @@ def main():
     ap.add_argument("--points", type=int, default=120000, help="points per scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--st-slots", type=int, default=0, help="key-grid slots of the streaming kernel (A/B runs)")
     ap.add_argument("--pf-dist", type=int, default=-1, help="bulk L2 prefetch distance in steps (A/B runs)")
     ap.add_argument("--hg-cfg", type=int, default=0, help="half-grid launch shape (A/B runs)")
-    ap.add_argument("--k1-impl", type=int, default=0, help="0 auto, 1 L2-key kernel, 2 half-grid kernel (A/B runs)")
+    ap.add_argument("--k1-impl", type=int, default=0, help="0 streaming kernel (default), 1 chunked L2-key kernels, 2 half-grid kernel (A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

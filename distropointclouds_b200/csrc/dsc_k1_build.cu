@@ -366,6 +366,175 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
     }
 }
 
+
+// ---- K1 streaming path: one visit per point, key grid resident in L2 ----------------------------------
+// Persistent CTAs pull 2048-point tiles from a global cursor in scan-major order, bin every point once and
+// fold it into the scan's key grid with RED.MAX (fire and forget: no return value, no dependent stall).
+// The key grids live in a small ring of slots that stays L2-resident (only a handful of scans are in
+// flight at any time), so HBM sees each point once and each output cell once.  The CTA that retires the
+// last tile of a scan decodes that scan's keys to floats (coalesced 128-bit stores), re-zeroes the slot
+// and publishes it for re-use.
+constexpr int ST_THREADS = 256;
+constexpr int ST_PPT = 8;
+constexpr int ST_TILE = ST_THREADS * ST_PPT;    // 2048 points = 32 KB
+
+struct StreamSync {            // zeroed before every launch
+    unsigned long long cursor;  // next global tile index
+    unsigned int pad[2];
+    // followed by: unsigned tiles_done[n_scans]; unsigned decoded[n_scans];
+};
+
+template <bool FAST, int VARIANT, bool FULL>
+__device__ __forceinline__ void st_point(const BinCfg &cfg, const float4 v, uint32_t *__restrict__ grid,
+                                         unsigned &n_clamped, unsigned long long *__restrict__ st)
+{
+    int ring, sector;
+    bool beyond, ok = false;
+    if constexpr (FAST) {
+        ok = dsc::screened_core(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
+        if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
+    }
+    float zv = FULL ? v.z : __fadd_rn(v.z, cfg.offset);
+    if (!ok) {                                   // near a bin boundary, zero / non-finite coordinate, ...
+        ExactArgs ea;
+        ea.R = cfg.R; ea.S = cfg.S; ea.pow2 = cfg.pow2; ea.gap_f32 = cfg.gap_f32;
+        ea.inv_gap_ring_f = cfg.inv_gap_ring_f; ea.inv_gap_sector_f = cfg.inv_gap_sector_f;
+        ea.gap_ring_f = cfg.gap_ring_f; ea.gap_sector_f = cfg.gap_sector_f;
+        ea.max_length_f = cfg.max_length_f; ea.offset = cfg.offset;
+        ea.gap_ring_d = cfg.gap_ring_d; ea.gap_sector_d = cfg.gap_sector_d;
+        const uint2 b = hg_bin_exact<VARIANT, FULL>(v.x, v.y, v.z, ea);
+        const int status = (int)(b.x >> 27), cell = (int)(b.x & 0x7ffffffu);
+        if (st) {                                // rare events: straight to the per-scan counters
+            if (FAST) atomicAdd(st + 5, 1ull);
+            if (status == dsc::PT_NONFINITE) atomicAdd(st + 1, 1ull);
+            if (status == dsc::PT_SECTOR_OVERFLOW) atomicAdd(st + 2, 1ull);
+            if (status == dsc::PT_OUT_OF_RANGE) atomicAdd(st + 4, 1ull);
+        }
+        if (status > dsc::PT_CLAMPED) return;
+        n_clamped += (status == dsc::PT_CLAMPED);
+        zv = __uint_as_float(b.y);
+        ring = 0;
+        sector = cell;                           // ring * S + sector below collapses to `cell`
+    } else {
+        if (VARIANT == 1 && beyond) {
+            if (st) atomicAdd(st + 4, 1ull);
+            return;
+        }
+        if (VARIANT == 0) n_clamped += beyond;
+    }
+    const uint32_t u = __float_as_uint(zv);
+    const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
+    if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
+    if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
+    atomicMax(grid + ring * cfg.S + sector, key);   // result unused => RED.MAX
+}
+
+template <bool FAST, int VARIANT, bool FULL>
+__global__ void __launch_bounds__(ST_THREADS, 4)
+k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
+          const int64_t *__restrict__ tile_base, int n_scans, long long total_tiles, int tiles_uniform,
+          uint32_t *__restrict__ keys, int n_slots, float *__restrict__ out,
+          unsigned long long *__restrict__ stats, StreamSync *__restrict__ sync, const BinCfg cfg)
+{
+    __shared__ long long s_tile;
+    __shared__ int s_scan, s_last;
+    const int tid = threadIdx.x;
+    const int cells = cfg.R * cfg.S;
+    unsigned *tiles_done = reinterpret_cast<unsigned *>(sync + 1);
+    unsigned *decoded = tiles_done + n_scans;
+    long long g = 0;
+    if (tid == 0) g = (long long)atomicAdd(&sync->cursor, 1ull);
+    for (;;) {
+        if (tid == 0) {
+            int scan = 0;
+            long long tile = -1;
+            if (g < total_tiles) {
+                if (tiles_uniform > 0) {
+                    scan = (int)(g / tiles_uniform);
+                    tile = g - (long long)scan * tiles_uniform;
+                } else {                         // ragged batch: tile_base[s] = first global tile of scan s
+                    int lo = 0, hi = n_scans;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (tile_base[mid] <= g) lo = mid; else hi = mid;
+                    }
+                    scan = lo;
+                    tile = g - tile_base[lo];
+                }
+                // slot re-use: the scan that used this slot n_slots scans ago must have been decoded and
+                // its slot re-zeroed.  It practically always is (scan-major order leaves dozens of scans of
+                // slack); the wait makes it a guarantee.  The decoder CTA is resident, so it terminates.
+                if (scan >= n_slots) {
+                    while (*reinterpret_cast<volatile unsigned *>(decoded + (scan - n_slots)) == 0u) __nanosleep(64);
+                    __threadfence();
+                }
+            }
+            s_tile = tile;
+            s_scan = scan;
+            g = (long long)atomicAdd(&sync->cursor, 1ull);   // next tile: the round trip hides behind this one
+        }
+        __syncthreads();
+        const long long tile = s_tile;
+        const int scan = s_scan;
+        if (tile < 0) break;
+        const int64_t p0 = offsets[scan];
+        const int n = (int)(offsets[scan + 1] - p0);
+        const int start = (int)tile * ST_TILE;
+        const int in_tile = min(n - start, ST_TILE);
+        uint32_t *grid = keys + (size_t)(scan % n_slots) * cells;
+        unsigned long long *st = stats ? stats + (int64_t)scan * 6 : nullptr;
+        const float4 *src = reinterpret_cast<const float4 *>(pts + (p0 + start) * 16) + tid;
+        float4 v[ST_PPT];
+        unsigned n_clamped = 0;
+        if (in_tile == ST_TILE) {
+#pragma unroll
+            for (int k = 0; k < ST_PPT; ++k) v[k] = ld_stream_f4(src + k * ST_THREADS);
+#pragma unroll
+            for (int k = 0; k < ST_PPT; ++k) st_point<FAST, VARIANT, FULL>(cfg, v[k], grid, n_clamped, st);
+        } else {
+#pragma unroll
+            for (int k = 0; k < ST_PPT; ++k)
+                if (k * ST_THREADS + tid < in_tile) v[k] = ld_stream_f4(src + k * ST_THREADS);
+#pragma unroll
+            for (int k = 0; k < ST_PPT; ++k)
+                if (k * ST_THREADS + tid < in_tile) st_point<FAST, VARIANT, FULL>(cfg, v[k], grid, n_clamped, st);
+        }
+        if (st) {
+            const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
+            if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
+            if (tid == 0) atomicAdd(st + 0, (unsigned long long)in_tile);
+        }
+        // ---- retire the tile; the CTA that retires the scan's last tile decodes the scan ----
+        __threadfence();                         // our REDs are performed before the counter moves
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned ntiles = (unsigned)((n + ST_TILE - 1) / ST_TILE);
+            const unsigned done = atomicAdd(tiles_done + scan, 1u) + 1u;
+            s_last = done == ntiles;
+            if (s_last) __threadfence();
+        }
+        __syncthreads();
+        if (s_last) {
+            uint4 *kq = reinterpret_cast<uint4 *>(grid);
+            float4 *oq = reinterpret_cast<float4 *>(out + (size_t)scan * cells);
+            const int nvec = cells >> 2;         // host guarantees cells % 4 == 0 and 16-byte aligned out
+            for (int i = tid; i < nvec; i += ST_THREADS) {
+                const uint4 q = __ldcg(kq + i);  // L2: the other CTAs' REDs landed there
+                float4 f;
+                f.x = dsc::key_to_float(q.x);
+                f.y = dsc::key_to_float(q.y);
+                f.z = dsc::key_to_float(q.z);
+                f.w = dsc::key_to_float(q.w);
+                __stcs(oq + i, f);
+                __stcg(kq + i, make_uint4(0, 0, 0, 0));
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(decoded + scan, 1u);
+        }
+    }
+}
+
 // keys -> float grid (coalesced 128-bit), and re-zero the scratch for the next chunk.
 __global__ void __launch_bounds__(256)
 k1_decode(uint32_t *__restrict__ keys, float *__restrict__ out, int64_t n_vec4)
@@ -503,6 +672,18 @@ static int normalize_device(dsc_ctx *ctx, const float *grids, int n, int64_t cel
     return DSC_OK;
 }
 
+static int dsc_reserve_sync(dsc_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->sync_cap) return DSC_OK;
+    if (ctx->sync_buf) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->sync_buf); }
+    ctx->sync_buf = nullptr;
+    ctx->sync_cap = 0;
+    const size_t cap = bytes * 2 + 4096;
+    DSC_CUDA(ctx, cudaMalloc(&ctx->sync_buf, cap));
+    ctx->sync_cap = cap;
+    return DSC_OK;
+}
+
 // Device-resident batch: pts/out/stats are device pointers, offsets already on the device.
 static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, const int64_t *d_offsets,
                         const int64_t *h_offsets, int n_scans, int stride, float *out, float *out_norm,
@@ -516,11 +697,74 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
     int rc;
     if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
-    // ---- main path: shared-memory half grids, one CTA pair per scan, persistent over the batch ----
+    // ---- streaming path: persistent single-visit kernel, key grids in an L2-resident slot ring ----
+    const bool st_ok = vec16 && (cells % 4) == 0 && (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1 &&
+                       ctx->k1_impl != 2;
+    if (st_ok) {
+        int n_slots = ctx->st_slots;
+        if (n_slots > n_scans) n_slots = n_scans;
+        const size_t need = (size_t)n_slots * cells * 4;
+        if (need > ctx->keys_bytes) {
+            if (ctx->keys) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->keys); }
+            ctx->keys = nullptr;
+            ctx->keys_bytes = 0;
+            DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
+            ctx->keys_bytes = need;
+            DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
+        }
+        // tile table
+        long long total_tiles = 0;
+        int uniform = -1;
+        for (int s = 0; s < n_scans; ++s) {
+            const long long t = (h_offsets[s + 1] - h_offsets[s] + ST_TILE - 1) / ST_TILE;
+            if (s == 0) uniform = (int)t; else if (t != uniform) uniform = 0;
+            total_tiles += t;
+        }
+        const size_t sync_bytes = sizeof(StreamSync) + sizeof(unsigned) * 2 * (size_t)n_scans;
+        const size_t tb_bytes = uniform > 0 ? 0 : sizeof(int64_t) * ((size_t)n_scans + 1);
+        if ((rc = dsc_reserve_sync(ctx, sync_bytes + tb_bytes + 64))) return rc;
+        StreamSync *sync = (StreamSync *)ctx->sync_buf;
+        int64_t *d_tb = nullptr;
+        if (uniform <= 0) {
+            d_tb = (int64_t *)((uint8_t *)ctx->sync_buf + ((sync_bytes + 15) & ~(size_t)15));
+            std::vector<int64_t> tb((size_t)n_scans + 1);
+            long long acc_t = 0;
+            for (int s = 0; s < n_scans; ++s) { tb[s] = acc_t; acc_t += (h_offsets[s + 1] - h_offsets[s] + ST_TILE - 1) / ST_TILE; }
+            tb[n_scans] = acc_t;
+            // pageable source: the copy is staged by the driver before the call returns
+            DSC_CUDA(ctx, cudaMemcpyAsync(d_tb, tb.data(), tb_bytes, cudaMemcpyHostToDevice, st));
+        }
+        DSC_CUDA(ctx, cudaMemsetAsync(sync, 0, sync_bytes, st));
+        if (total_tiles > 0) {
+            unsigned long long *stp = (unsigned long long *)stats;
+            int grid_ctas = ctx->sm_count * 4;
+            if ((long long)grid_ctas > total_tiles) grid_ctas = (int)total_tiles;
+#define ST_LAUNCH(F, V, H)                                                                                      \
+    k1_stream<F, V, H><<<grid_ctas, ST_THREADS, 0, st>>>(pts, d_offsets, d_tb, n_scans, total_tiles, uniform,     \
+                                                         ctx->keys, n_slots, out, stp, sync, cfg)
+            const bool full = p->full_height != 0;
+            if (cfg.fast_ok) {
+                if (p->variant == 0) { if (full) ST_LAUNCH(true, 0, true); else ST_LAUNCH(true, 0, false); }
+                else                 { if (full) ST_LAUNCH(true, 1, true); else ST_LAUNCH(true, 1, false); }
+            } else {
+                if (p->variant == 0) { if (full) ST_LAUNCH(false, 0, true); else ST_LAUNCH(false, 0, false); }
+                else                 { if (full) ST_LAUNCH(false, 1, true); else ST_LAUNCH(false, 1, false); }
+            }
+#undef ST_LAUNCH
+            if ((rc = dsc_check_launch(ctx, "k1_stream"))) return rc;
+        }
+        // scans without points never retire a tile: their grids are all zeros
+        for (int s = 0; s < n_scans; ++s)
+            if (h_offsets[s + 1] == h_offsets[s])
+                DSC_CUDA(ctx, cudaMemsetAsync(out + (size_t)s * cells, 0, (size_t)cells * 4, st));
+        if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
+        return DSC_OK;
+    }
+    // ---- shared-memory half grids, one CTA pair per scan, persistent over the batch (A/B variant) ----
     const size_t hg_smem = (size_t)cells * 2;   // R * S/2 * 4 bytes
     const bool hg_ok = vec16 && (p->num_sector % 8) == 0 && hg_smem <= ctx->smem_optin &&
                        (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1 &&
-                       (ctx->k1_impl == 2 || n_scans >= ctx->sm_count / 8);
+                       ctx->k1_impl == 2;
     if (hg_ok) {
         int pairs = ctx->sm_count / 2;
         if (pairs > n_scans) pairs = n_scans;
@@ -660,6 +904,9 @@ void dsc_k1_release(dsc_ctx *ctx)
     if (ctx->d_offsets) cudaFree(ctx->d_offsets);
     if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
     if (ctx->minmax) cudaFree(ctx->minmax);
+    if (ctx->sync_buf) cudaFree(ctx->sync_buf);
+    ctx->sync_buf = nullptr;
+    ctx->sync_cap = 0;
     ctx->keys = nullptr;
     ctx->d_offsets = nullptr;
     ctx->h_offsets = nullptr;
