@@ -150,6 +150,7 @@ def run_ours(args):
     eng.set_option("hg_cfg", args.hg_cfg)
     if args.pf_dist >= 0:
         eng.set_option("pf_dist", args.pf_dist)
+    eng.set_option("st_cfg", args.st_cfg)
     if args.st_slots > 0:
         eng.set_option("st_slots", args.st_slots)
     params = ScanContextParams(R, S, MAXLEN)
@@ -267,6 +268,7 @@ def main():
     ap.add_argument("--points", type=int, default=120000, help="points per scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--st-cfg", type=int, default=0, help="streaming kernel shape (A/B runs)")
     ap.add_argument("--st-slots", type=int, default=0, help="key-grid slots of the streaming kernel (A/B runs)")
     ap.add_argument("--pf-dist", type=int, default=-1, help="bulk L2 prefetch distance in steps (A/B runs)")
     ap.add_argument("--hg-cfg", type=int, default=0, help="half-grid launch shape (A/B runs)")

@@ -17,6 +17,7 @@ struct dsc_ctx {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
+    int st_cfg = 0;                  // streaming kernel shape: 0 = 8 pts/thread, 3 CTAs/SM; 1 = 6 pts/thread, 4 CTAs/SM
     int st_slots = 64;               // key-grid slots of the streaming kernel (L2-resident ring)
     void *sync_buf = nullptr;        // streaming kernel: cursor, per-scan counters, tile table
     size_t sync_cap = 0;

@@ -160,16 +160,18 @@ __device__ __forceinline__ void reds_max_u32(uint32_t addr, uint32_t v)
 
 // The fdlibm chain is ~150 instructions and runs for < 1 % of the points: keep it out of line so the
 // streaming loop stays small (instruction cache) and its registers do not count against the hot path.
-// Everything crosses the call boundary by value (a BinCfg reference would force the caller's copy of
-// the configuration into local memory); the result is packed: x = status << 27 | cell, y = bits of z.
+// Its configuration is parked in shared memory once per CTA (a BinCfg reference would force the
+// caller's copy into local memory, by-value arguments cost registers at every call site); the result
+// is packed: x = status << 27 | cell, y = bits of z.
 struct ExactArgs {
     int R, S, pow2, gap_f32;
     float inv_gap_ring_f, inv_gap_sector_f, gap_ring_f, gap_sector_f, max_length_f, offset;
     double gap_ring_d, gap_sector_d;
 };
 template <int VARIANT, bool FULL>
-__device__ __noinline__ uint2 hg_bin_exact(float x, float y, float z, const ExactArgs a)
+__device__ __noinline__ uint2 hg_bin_exact(float x, float y, float z, const ExactArgs *__restrict__ ap)
 {
+    const ExactArgs a = *ap;                     // lives in shared memory, filled once per CTA
     BinCfg c;
     c.R = a.R; c.S = a.S; c.variant = VARIANT; c.full_height = FULL; c.offset = a.offset;
     c.pow2 = a.pow2; c.gap_f32 = a.gap_f32;
@@ -179,6 +181,15 @@ __device__ __noinline__ uint2 hg_bin_exact(float x, float y, float z, const Exac
     c.max_length_f = a.max_length_f;
     const BinResult b = dsc::bin_exact(c, x, y, z);
     return make_uint2(((uint32_t)b.status << 27) | (uint32_t)b.cell, __float_as_uint(b.z));
+}
+
+__device__ __forceinline__ void fill_exact_args(ExactArgs *ea, const BinCfg &cfg)
+{
+    ea->R = cfg.R; ea->S = cfg.S; ea->pow2 = cfg.pow2; ea->gap_f32 = cfg.gap_f32;
+    ea->inv_gap_ring_f = cfg.inv_gap_ring_f; ea->inv_gap_sector_f = cfg.inv_gap_sector_f;
+    ea->gap_ring_f = cfg.gap_ring_f; ea->gap_sector_f = cfg.gap_sector_f;
+    ea->max_length_f = cfg.max_length_f; ea->offset = cfg.offset;
+    ea->gap_ring_d = cfg.gap_ring_d; ea->gap_sector_d = cfg.gap_sector_d;
 }
 
 // Bulk L2 prefetch (UBLKPF.L2, the TMA engine): shared memory is entirely taken by the key grid, so
@@ -216,7 +227,8 @@ struct HgConst {
 };
 
 template <bool FAST, int VARIANT, bool FULL>
-__device__ __forceinline__ void hg_point(const BinCfg &cfg, const HgConst &k, const float4 v, StatAcc &acc)
+__device__ __forceinline__ void hg_point(const BinCfg &cfg, const HgConst &k, const ExactArgs *ea, const float4 v,
+                                         StatAcc &acc)
 {
     // ---- whose point is it?  S/2 sectors are exactly 180 degrees, so it is sign(y) except within a
     // hair of the seam, where both CTAs evaluate the point and the computed sector decides.  Variant A
@@ -235,12 +247,6 @@ __device__ __forceinline__ void hg_point(const BinCfg &cfg, const HgConst &k, co
     bool dropped = false;
     int drop_status = 0;
     if (!ok) {                                   // near a bin boundary, zero / non-finite coordinate, ...
-        ExactArgs ea;
-        ea.R = cfg.R; ea.S = cfg.S; ea.pow2 = cfg.pow2; ea.gap_f32 = cfg.gap_f32;
-        ea.inv_gap_ring_f = cfg.inv_gap_ring_f; ea.inv_gap_sector_f = cfg.inv_gap_sector_f;
-        ea.gap_ring_f = cfg.gap_ring_f; ea.gap_sector_f = cfg.gap_sector_f;
-        ea.max_length_f = cfg.max_length_f; ea.offset = cfg.offset;
-        ea.gap_ring_d = cfg.gap_ring_d; ea.gap_sector_d = cfg.gap_sector_d;
         const uint2 b = hg_bin_exact<VARIANT, FULL>(v.x, v.y, v.z, ea);
         const int status = (int)(b.x >> 27), cell = (int)(b.x & 0x7ffffffu);
         ring = cell / cfg.S;
@@ -287,8 +293,10 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
 {
     constexpr int STEP = THREADS * U;           // points per step and register set
     extern __shared__ __align__(16) uint32_t sgrid[];
+    __shared__ ExactArgs s_ea;
     const BinCfg &cfg = cfg_in;                 // stays in the constant bank: its address is never taken
     const int tid = threadIdx.x;
+    if (tid == 0) fill_exact_args(&s_ea, cfg);
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     HgConst k;
     k.half = blockIdx.x & 1;
@@ -328,7 +336,7 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
 #pragma unroll
             for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * THREADS);
 #pragma unroll
-            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, a[u], acc);
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, &s_ea, a[u], acc);
             p += 2 * STEP;
             step += 2;
             if (step < nfull) {
@@ -336,14 +344,14 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
                 for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * THREADS);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, b[u], acc);
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, &s_ea, b[u], acc);
         }
         if (step < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, a[u], acc);
+            for (int u = 0; u < U; ++u) hg_point<FAST, VARIANT, FULL>(cfg, k, &s_ea, a[u], acc);
         }
         for (int i = nfull * STEP + tid; i < n; i += THREADS)              // ragged tail
-            hg_point<FAST, VARIANT, FULL>(cfg, k, ld_stream_f4(s4 + i), acc);
+            hg_point<FAST, VARIANT, FULL>(cfg, k, &s_ea, ld_stream_f4(s4 + i), acc);
         __syncthreads();
         // ---- one coalesced write-out of this CTA's half of every ring row, re-zeroing the keys ----
         float *o = out + (int64_t)scan * cfg.R * cfg.S + k.sector0;
@@ -375,18 +383,17 @@ k1_halfgrid(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets
 // last tile of a scan decodes that scan's keys to floats (coalesced 128-bit stores), re-zeroes the slot
 // and publishes it for re-use.
 constexpr int ST_THREADS = 256;
-constexpr int ST_PPT = 8;
-constexpr int ST_TILE = ST_THREADS * ST_PPT;    // 2048 points = 32 KB
 
 struct StreamSync {            // zeroed before every launch
-    unsigned long long cursor;  // next global tile index
-    unsigned int pad[2];
+    unsigned int cursor32;      // next global tile index
+    unsigned int pad[3];        // pad[0]: decode watermark (every scan below it is decoded)
     // followed by: unsigned tiles_done[n_scans]; unsigned decoded[n_scans];
 };
 
 template <bool FAST, int VARIANT, bool FULL>
-__device__ __forceinline__ void st_point(const BinCfg &cfg, const float4 v, uint32_t *__restrict__ grid,
-                                         unsigned &n_clamped, unsigned long long *__restrict__ st)
+__device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v,
+                                         uint32_t *__restrict__ grid, unsigned &n_clamped,
+                                         unsigned long long *__restrict__ stats, int scan)
 {
     int ring, sector;
     bool beyond, ok = false;
@@ -396,14 +403,9 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const float4 v, uint
     }
     float zv = FULL ? v.z : __fadd_rn(v.z, cfg.offset);
     if (!ok) {                                   // near a bin boundary, zero / non-finite coordinate, ...
-        ExactArgs ea;
-        ea.R = cfg.R; ea.S = cfg.S; ea.pow2 = cfg.pow2; ea.gap_f32 = cfg.gap_f32;
-        ea.inv_gap_ring_f = cfg.inv_gap_ring_f; ea.inv_gap_sector_f = cfg.inv_gap_sector_f;
-        ea.gap_ring_f = cfg.gap_ring_f; ea.gap_sector_f = cfg.gap_sector_f;
-        ea.max_length_f = cfg.max_length_f; ea.offset = cfg.offset;
-        ea.gap_ring_d = cfg.gap_ring_d; ea.gap_sector_d = cfg.gap_sector_d;
         const uint2 b = hg_bin_exact<VARIANT, FULL>(v.x, v.y, v.z, ea);
         const int status = (int)(b.x >> 27), cell = (int)(b.x & 0x7ffffffu);
+        unsigned long long *st = stats ? stats + (int64_t)scan * 6 : nullptr;
         if (st) {                                // rare events: straight to the per-scan counters
             if (FAST) atomicAdd(st + 5, 1ull);
             if (status == dsc::PT_NONFINITE) atomicAdd(st + 1, 1ull);
@@ -417,7 +419,7 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const float4 v, uint
         sector = cell;                           // ring * S + sector below collapses to `cell`
     } else {
         if (VARIANT == 1 && beyond) {
-            if (st) atomicAdd(st + 4, 1ull);
+            if (stats) atomicAdd(stats + (int64_t)scan * 6 + 4, 1ull);
             return;
         }
         if (VARIANT == 0) n_clamped += beyond;
@@ -429,60 +431,111 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const float4 v, uint
     atomicMax(grid + ring * cfg.S + sector, key);   // result unused => RED.MAX
 }
 
-template <bool FAST, int VARIANT, bool FULL>
-__global__ void __launch_bounds__(ST_THREADS, 4)
+// keys (L2) -> float grid (HBM, coalesced 128-bit streaming stores); re-zeroes the slot.  Out of line so
+// that its 8-deep load pipeline does not share the streaming loop's register budget.
+__device__ __noinline__ void st_decode(uint32_t *__restrict__ grid, float *__restrict__ out, int nvec, int tid)
+{
+    const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
+    uint4 *kz = reinterpret_cast<uint4 *>(grid);
+    float4 *oq = reinterpret_cast<float4 *>(out);
+    constexpr int DU = 8;                        // 8 x 128-bit L2 loads in flight per thread
+    for (int i0 = tid; i0 < nvec; i0 += ST_THREADS * DU) {
+        uint4 q[DU];
+#pragma unroll
+        for (int d = 0; d < DU; ++d) {
+            const int i = i0 + d * ST_THREADS;
+            if (i < nvec) q[d] = __ldcg(kq + i);  // L2: where the other CTAs' REDs landed
+        }
+#pragma unroll
+        for (int d = 0; d < DU; ++d) {
+            const int i = i0 + d * ST_THREADS;
+            if (i < nvec) {
+                float4 f;
+                f.x = dsc::key_to_float(q[d].x);
+                f.y = dsc::key_to_float(q[d].y);
+                f.z = dsc::key_to_float(q[d].z);
+                f.w = dsc::key_to_float(q[d].w);
+                __stcs(oq + i, f);
+                __stcg(kz + i, make_uint4(0, 0, 0, 0));
+            }
+        }
+    }
+}
+
+// slot re-use guard: scan `need` must be decoded and its slot re-zeroed before the slot is written again.
+// The watermark (every scan below it is decoded) is far ahead in practice and cached per CTA; the decoder
+// of `need` is a running CTA, so the wait terminates.
+__device__ __forceinline__ void st_wait_slot(StreamSync *sync, const unsigned *decoded, int need, unsigned &water)
+{
+    if (need < 0 || (unsigned)need < water) return;
+    for (;;) {
+        water = *reinterpret_cast<volatile unsigned *>(&sync->pad[0]);
+        if ((unsigned)need < water) break;
+        if (*reinterpret_cast<const volatile unsigned *>(decoded + need) != 0u) break;
+        __nanosleep(64);
+    }
+    __threadfence();
+}
+
+// tile -> (scan, tile in scan)
+__device__ __forceinline__ void st_locate(int g, const int64_t *__restrict__ tile_base, int n_scans,
+                                          int tiles_uniform, int &scan, int &tile)
+{
+    if (tiles_uniform > 0) {
+        scan = g / tiles_uniform;
+        tile = g - scan * tiles_uniform;
+    } else {                                     // ragged batch: tile_base[s] = first global tile of scan s
+        int lo = 0, hi = n_scans;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tile_base[mid] <= g) lo = mid; else hi = mid;
+        }
+        scan = lo;
+        tile = (int)(g - tile_base[lo]);
+    }
+}
+
+template <bool FAST, int VARIANT, bool FULL, int ST_PPT, int MINB>
+__global__ void __launch_bounds__(ST_THREADS, MINB)
 k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
-          const int64_t *__restrict__ tile_base, int n_scans, long long total_tiles, int tiles_uniform,
+          const int64_t *__restrict__ tile_base, int n_scans, int total_tiles, int tiles_uniform,
           uint32_t *__restrict__ keys, int n_slots, float *__restrict__ out,
           unsigned long long *__restrict__ stats, StreamSync *__restrict__ sync, const BinCfg cfg)
 {
-    __shared__ long long s_tile;
-    __shared__ int s_scan, s_last;
+    constexpr int ST_TILE = ST_THREADS * ST_PPT;
+    __shared__ int s_tile, s_scan, s_last;
+    __shared__ ExactArgs s_ea;
     const int tid = threadIdx.x;
     const int cells = cfg.R * cfg.S;
+    if (tid == 0) fill_exact_args(&s_ea, cfg);
     unsigned *tiles_done = reinterpret_cast<unsigned *>(sync + 1);
     unsigned *decoded = tiles_done + n_scans;
-    long long g = 0;
-    if (tid == 0) g = (long long)atomicAdd(&sync->cursor, 1ull);
-    for (;;) {
-        if (tid == 0) {
-            int scan = 0;
-            long long tile = -1;
-            if (g < total_tiles) {
-                if (tiles_uniform > 0) {
-                    scan = (int)(g / tiles_uniform);
-                    tile = g - (long long)scan * tiles_uniform;
-                } else {                         // ragged batch: tile_base[s] = first global tile of scan s
-                    int lo = 0, hi = n_scans;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (tile_base[mid] <= g) lo = mid; else hi = mid;
-                    }
-                    scan = lo;
-                    tile = g - tile_base[lo];
-                }
-                // slot re-use: the scan that used this slot n_slots scans ago must have been decoded and
-                // its slot re-zeroed.  It practically always is (scan-major order leaves dozens of scans of
-                // slack); the wait makes it a guarantee.  The decoder CTA is resident, so it terminates.
-                if (scan >= n_slots) {
-                    while (*reinterpret_cast<volatile unsigned *>(decoded + (scan - n_slots)) == 0u) __nanosleep(64);
-                    __threadfence();
-                }
-            }
-            s_tile = tile;
-            s_scan = scan;
-            g = (long long)atomicAdd(&sync->cursor, 1ull);   // next tile: the round trip hides behind this one
+    // thread 0 is the CTA's scheduler; `g` is always fetched one tile ahead so that the round trip of
+    // the cursor atomic hides behind the current tile, `water` caches the decode watermark
+    int g = 0;
+    unsigned water = 0;
+    if (tid == 0) {
+        g = (int)atomicAdd(&sync->cursor32, 1u);
+        s_last = 0;
+        int scan = 0, tile = -1;
+        if (g < total_tiles) {
+            st_locate(g, tile_base, n_scans, tiles_uniform, scan, tile);
+            st_wait_slot(sync, decoded, scan - n_slots, water);
         }
-        __syncthreads();
-        const long long tile = s_tile;
+        s_tile = tile;
+        s_scan = scan;
+        g = (int)atomicAdd(&sync->cursor32, 1u);
+    }
+    __syncthreads();
+    for (;;) {
+        const int tile = s_tile;
         const int scan = s_scan;
         if (tile < 0) break;
         const int64_t p0 = offsets[scan];
         const int n = (int)(offsets[scan + 1] - p0);
-        const int start = (int)tile * ST_TILE;
+        const int start = tile * ST_TILE;
         const int in_tile = min(n - start, ST_TILE);
         uint32_t *grid = keys + (size_t)(scan % n_slots) * cells;
-        unsigned long long *st = stats ? stats + (int64_t)scan * 6 : nullptr;
         const float4 *src = reinterpret_cast<const float4 *>(pts + (p0 + start) * 16) + tid;
         float4 v[ST_PPT];
         unsigned n_clamped = 0;
@@ -490,47 +543,67 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
 #pragma unroll
             for (int k = 0; k < ST_PPT; ++k) v[k] = ld_stream_f4(src + k * ST_THREADS);
 #pragma unroll
-            for (int k = 0; k < ST_PPT; ++k) st_point<FAST, VARIANT, FULL>(cfg, v[k], grid, n_clamped, st);
+            for (int k = 0; k < ST_PPT; ++k) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, v[k], grid, n_clamped, stats, scan);
         } else {
 #pragma unroll
             for (int k = 0; k < ST_PPT; ++k)
                 if (k * ST_THREADS + tid < in_tile) v[k] = ld_stream_f4(src + k * ST_THREADS);
 #pragma unroll
             for (int k = 0; k < ST_PPT; ++k)
-                if (k * ST_THREADS + tid < in_tile) st_point<FAST, VARIANT, FULL>(cfg, v[k], grid, n_clamped, st);
+                if (k * ST_THREADS + tid < in_tile) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, v[k], grid, n_clamped, stats, scan);
         }
-        if (st) {
+        if (stats) {
+            unsigned long long *st = stats + (int64_t)scan * 6;
             const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
             if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
             if (tid == 0) atomicAdd(st + 0, (unsigned long long)in_tile);
         }
-        // ---- retire the tile; the CTA that retires the scan's last tile decodes the scan ----
-        __threadfence();                         // our REDs are performed before the counter moves
-        __syncthreads();
+        // ---- retire the tile and pick the next one (one barrier pair per tile) ----
+        __syncthreads();                         // every thread has issued its REDs
         if (tid == 0) {
+            __threadfence();                     // release: the CTA's REDs are performed before the count moves
             const unsigned ntiles = (unsigned)((n + ST_TILE - 1) / ST_TILE);
             const unsigned done = atomicAdd(tiles_done + scan, 1u) + 1u;
             s_last = done == ntiles;
-            if (s_last) __threadfence();
+            if (done == ntiles) __threadfence(); // acquire: the other CTAs' REDs of this scan are visible
+            int nscan = 0, ntile = -1;
+            if (done != ntiles) {                // (a decoding CTA picks its next tile after the decode)
+                if (g < total_tiles) {
+                    st_locate(g, tile_base, n_scans, tiles_uniform, nscan, ntile);
+                    st_wait_slot(sync, decoded, nscan - n_slots, water);
+                }
+                s_tile = ntile;
+                s_scan = nscan;
+                g = (int)atomicAdd(&sync->cursor32, 1u);
+            }
         }
         __syncthreads();
         if (s_last) {
-            uint4 *kq = reinterpret_cast<uint4 *>(grid);
-            float4 *oq = reinterpret_cast<float4 *>(out + (size_t)scan * cells);
-            const int nvec = cells >> 2;         // host guarantees cells % 4 == 0 and 16-byte aligned out
-            for (int i = tid; i < nvec; i += ST_THREADS) {
-                const uint4 q = __ldcg(kq + i);  // L2: the other CTAs' REDs landed there
-                float4 f;
-                f.x = dsc::key_to_float(q.x);
-                f.y = dsc::key_to_float(q.y);
-                f.z = dsc::key_to_float(q.z);
-                f.w = dsc::key_to_float(q.w);
-                __stcs(oq + i, f);
-                __stcg(kq + i, make_uint4(0, 0, 0, 0));
+            // ---- this CTA retired the scan's last tile: decode it, re-zero the slot, publish ----
+            st_decode(grid, out + (size_t)scan * cells, cells >> 2, tid);
+            __syncthreads();                     // all zeroing stores issued
+            if (tid == 0) {
+                __threadfence();                 // release the re-zeroed slot
+                atomicExch(decoded + scan, 1u);
+                __threadfence();
+                // advance the watermark over every leading decoded scan
+                unsigned w = *reinterpret_cast<volatile unsigned *>(&sync->pad[0]);
+                while (w < (unsigned)n_scans && *reinterpret_cast<volatile unsigned *>(decoded + w) != 0u) {
+                    const unsigned prev = atomicCAS(&sync->pad[0], w, w + 1u);
+                    w = prev == w ? w + 1u : prev;
+                }
+                // now pick this CTA's next tile
+                int nscan = 0, ntile = -1;
+                if (g < total_tiles) {
+                    st_locate(g, tile_base, n_scans, tiles_uniform, nscan, ntile);
+                    st_wait_slot(sync, decoded, nscan - n_slots, water);
+                }
+                s_tile = ntile;
+                s_scan = nscan;
+                s_last = 0;
+                g = (int)atomicAdd(&sync->cursor32, 1u);
             }
-            __threadfence();
             __syncthreads();
-            if (tid == 0) atomicExch(decoded + scan, 1u);
         }
     }
 }
@@ -713,6 +786,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
         }
         // tile table
+        const int ST_TILE = ST_THREADS * (ctx->st_cfg == 1 ? 6 : 8);
         long long total_tiles = 0;
         int uniform = -1;
         for (int s = 0; s < n_scans; ++s) {
@@ -735,13 +809,20 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             DSC_CUDA(ctx, cudaMemcpyAsync(d_tb, tb.data(), tb_bytes, cudaMemcpyHostToDevice, st));
         }
         DSC_CUDA(ctx, cudaMemsetAsync(sync, 0, sync_bytes, st));
+        if (total_tiles > 0x7fff0000LL) DSC_FAIL(ctx, DSC_ERR_INVALID, "batch too large for one call");
         if (total_tiles > 0) {
             unsigned long long *stp = (unsigned long long *)stats;
-            int grid_ctas = ctx->sm_count * 4;
+            const int minb = ctx->st_cfg == 1 ? 4 : 3;
+            int grid_ctas = ctx->sm_count * minb;
             if ((long long)grid_ctas > total_tiles) grid_ctas = (int)total_tiles;
+#define ST_LAUNCH2(F, V, H, PPT, MINB)                                                                          \
+    k1_stream<F, V, H, PPT, MINB><<<grid_ctas, ST_THREADS, 0, st>>>(pts, d_offsets, d_tb, n_scans,              \
+                                                                    (int)total_tiles, uniform, ctx->keys,       \
+                                                                    n_slots, out, stp, sync, cfg)
 #define ST_LAUNCH(F, V, H)                                                                                      \
-    k1_stream<F, V, H><<<grid_ctas, ST_THREADS, 0, st>>>(pts, d_offsets, d_tb, n_scans, total_tiles, uniform,     \
-                                                         ctx->keys, n_slots, out, stp, sync, cfg)
+    do {                                                                                                        \
+        if (ctx->st_cfg == 1) ST_LAUNCH2(F, V, H, 6, 4); else ST_LAUNCH2(F, V, H, 8, 3);                        \
+    } while (0)
             const bool full = p->full_height != 0;
             if (cfg.fast_ok) {
                 if (p->variant == 0) { if (full) ST_LAUNCH(true, 0, true); else ST_LAUNCH(true, 0, false); }
@@ -751,6 +832,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
                 else                 { if (full) ST_LAUNCH(false, 1, true); else ST_LAUNCH(false, 1, false); }
             }
 #undef ST_LAUNCH
+#undef ST_LAUNCH2
             if ((rc = dsc_check_launch(ctx, "k1_stream"))) return rc;
         }
         // scans without points never retire a tile: their grids are all zeros
