@@ -151,6 +151,7 @@ def run_ours(args):
     if args.pf_dist >= 0:
         eng.set_option("pf_dist", args.pf_dist)
     eng.set_option("st_cfg", args.st_cfg)
+    eng.set_option("sc_cfg", args.sc_cfg)
     if args.st_slots > 0:
         eng.set_option("st_slots", args.st_slots)
     params = ScanContextParams(R, S, MAXLEN)
@@ -238,7 +239,7 @@ def run_ours(args):
         }
         if args.skip_e2e:
             line["e2e"] = None
-        line["config"]["k1_impl"] = {0: "stream", 1: "l2keys", 2: "halfgrid"}[args.k1_impl]
+        line["config"]["k1_impl"] = {0: "auto", 1: "l2keys", 2: "halfgrid", 3: "scan", 4: "tile"}[args.k1_impl]
         if world == 1 and not args.no_cpu_baseline and h_pts is not None:
             from oracle import oracle as orc
             cores = orc.max_threads()
@@ -268,6 +269,7 @@ def main():
     ap.add_argument("--points", type=int, default=120000, help="points per scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--sc-cfg", type=int, default=0, help="scan kernel shape (A/B runs)")
     ap.add_argument("--st-cfg", type=int, default=0, help="streaming kernel shape (A/B runs)")
     ap.add_argument("--st-slots", type=int, default=0, help="key-grid slots of the streaming kernel (A/B runs)")
     ap.add_argument("--pf-dist", type=int, default=-1, help="bulk L2 prefetch distance in steps (A/B runs)")

@@ -73,7 +73,8 @@ extern "C" int dsc_set_timing(dsc_ctx *ctx, int enabled)
 extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return DSC_ERR_INVALID;
-    if (!strcmp(name, "k1_impl") && value >= 0 && value <= 2) { ctx->k1_impl = (int)value; return DSC_OK; }
+    if (!strcmp(name, "k1_impl") && value >= 0 && value <= 4) { ctx->k1_impl = (int)value; return DSC_OK; }
+    if (!strcmp(name, "sc_cfg") && value >= 0 && value <= 1) { ctx->sc_cfg = (int)value; return DSC_OK; }
     if (!strcmp(name, "st_cfg") && value >= 0 && value <= 1) { ctx->st_cfg = (int)value; return DSC_OK; }
     if (!strcmp(name, "st_slots") && value >= 1 && value <= 4096) { ctx->st_slots = (int)value; return DSC_OK; }
     if (!strcmp(name, "pf_dist") && value >= 0 && value <= 64) { ctx->pf_dist = (int)value; return DSC_OK; }

@@ -17,13 +17,14 @@ struct dsc_ctx {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
+    int sc_cfg = 0;                  // scan kernel: 0 = 2 loads x 2 sets per thread, 1 = 3 x 2
     int st_cfg = 0;                  // streaming kernel shape: 0 = 8 pts/thread, 3 CTAs/SM; 1 = 6 pts/thread, 4 CTAs/SM
     int st_slots = 64;               // key-grid slots of the streaming kernel (L2-resident ring)
     void *sync_buf = nullptr;        // streaming kernel: cursor, per-scan counters, tile table
     size_t sync_cap = 0;
     int pf_dist = 0;                 // bulk L2 prefetch distance in steps (0 = off)
     int hg_cfg = 0;                  // half-grid launch shape: 0 = 1024 thr x 2 loads x 2 sets, 1 = 1024x3x2, 2 = 512x4x2 (A/B runs)
-    int k1_impl = 0;                 // 0 auto (streaming kernel), 1 chunked L2-key kernels, 2 half-grid kernel
+    int k1_impl = 0;                 // 0 auto, 1 chunked L2-key kernels, 2 half-grid, 3 scan-per-CTA, 4 tile kernel
     float last_ms = -1.0f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 

@@ -147,6 +147,11 @@ k1_build_keys(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offse
 // computed sector decides.  There is no traffic between the CTAs at all: reduction = local ATOMS.MAX,
 // write-out = one coalesced pass per scan that also re-zeroes the grid for the next scan.
 
+// fire-and-forget reduction at L2: no return value, nothing for the warp to wait on
+__device__ __forceinline__ void red_max_global(uint32_t *p, uint32_t v)
+{
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -428,7 +433,7 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea,
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
     if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
-    atomicMax(grid + ring * cfg.S + sector, key);   // result unused => RED.MAX
+    red_max_global(grid + ring * cfg.S + sector, key);
 }
 
 // keys (L2) -> float grid (HBM, coalesced 128-bit streaming stores); re-zeroes the slot.  Out of line so
@@ -608,6 +613,114 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
     }
 }
 
+
+// ---- K1 main path: one persistent CTA per scan, private L2-resident key slot ------------------------------
+// Every CTA owns one key grid in global memory (sm_count x 460 KB = 68 MB, resident in the 126 MB L2) and
+// processes whole scans: stream the points once (128-bit loads, two register sets ping-pong), bin each
+// point once, fold it into the slot with RED.MAX (fire and forget: no return value, no dependent stall,
+// no barrier in the loop).  When the scan is done the same CTA decodes the slot to floats (coalesced
+// 128-bit streaming stores), re-zeroes it and moves on.  There is no synchronisation between CTAs at all;
+// HBM sees each point once and each output cell once.
+constexpr int SC_THREADS = 1024;
+
+template <bool FAST, int VARIANT, bool FULL, int U>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
+        uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
+        unsigned int *__restrict__ cursor, const BinCfg cfg)
+{
+    constexpr int STEP = SC_THREADS * U;
+    __shared__ int s_next[2];
+    __shared__ ExactArgs s_ea;
+    const int tid = threadIdx.x;
+    const int cells = cfg.R * cfg.S;
+    const int nvec = cells >> 2;                 // host guarantees cells % 4 == 0
+    uint32_t *grid = keys + (size_t)blockIdx.x * cells;
+    if (tid == 0) {
+        fill_exact_args(&s_ea, cfg);
+        s_next[0] = (int)atomicAdd(cursor, 1u);
+    }
+    __syncthreads();
+    int scan = s_next[0];
+    int par = 0;
+    while (scan < n_scans) {
+        // scan index after this one: fetched now, consumed after the scan (the round trip is hidden)
+        if (tid == 0) s_next[par ^ 1] = (int)atomicAdd(cursor, 1u);
+        const int64_t p0 = offsets[scan];
+        const int n = (int)(offsets[scan + 1] - p0);          // host guarantees < 2^31 points per scan
+        const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
+        unsigned n_clamped = 0;
+        const int nfull = n / STEP;
+        const float4 *p = s4 + tid;
+        float4 a[U], b[U];
+        if (nfull > 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * SC_THREADS);
+        }
+        int step = 0;
+        while (step + 1 < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * SC_THREADS);
+#pragma unroll
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan);
+            p += 2 * STEP;
+            step += 2;
+            if (step < nfull) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * SC_THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, b[u], grid, n_clamped, stats, scan);
+        }
+        if (step < nfull) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan);
+        }
+        for (int i = nfull * STEP + tid; i < n; i += SC_THREADS)              // ragged tail
+            st_point<FAST, VARIANT, FULL>(cfg, &s_ea, ld_stream_f4(s4 + i), grid, n_clamped, stats, scan);
+        if (stats) {
+            unsigned long long *st = stats + (int64_t)scan * 6;
+            const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
+            if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
+            if (tid == 0) atomicAdd(st + 0, (unsigned long long)n);
+        }
+        __threadfence();                         // our REDs are performed ...
+        __syncthreads();                         // ... before any thread of the CTA reads the slot back
+        // ---- decode: keys (L2) -> floats (HBM), re-zero the slot ----
+        {
+            const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
+            uint4 *kz = reinterpret_cast<uint4 *>(grid);
+            float4 *oq = reinterpret_cast<float4 *>(out + (size_t)scan * cells);
+            constexpr int DU = 4;
+            for (int i0 = tid; i0 < nvec; i0 += SC_THREADS * DU) {
+                uint4 q[DU];
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int i = i0 + d * SC_THREADS;
+                    if (i < nvec) q[d] = __ldcg(kq + i);
+                }
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int i = i0 + d * SC_THREADS;
+                    if (i < nvec) {
+                        float4 f;
+                        f.x = dsc::key_to_float(q[d].x);
+                        f.y = dsc::key_to_float(q[d].y);
+                        f.z = dsc::key_to_float(q[d].z);
+                        f.w = dsc::key_to_float(q[d].w);
+                        __stcs(oq + i, f);
+                        __stcg(kz + i, make_uint4(0, 0, 0, 0));
+                    }
+                }
+            }
+        }
+        __threadfence();                         // the zeroes are performed ...
+        __syncthreads();                         // ... before the next scan's REDs (also publishes s_next)
+        par ^= 1;
+        scan = s_next[par];
+    }
+}
+
 // keys -> float grid (coalesced 128-bit), and re-zero the scratch for the next chunk.
 __global__ void __launch_bounds__(256)
 k1_decode(uint32_t *__restrict__ keys, float *__restrict__ out, int64_t n_vec4)
@@ -770,9 +883,47 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
     int rc;
     if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
-    // ---- streaming path: persistent single-visit kernel, key grids in an L2-resident slot ring ----
-    const bool st_ok = vec16 && (cells % 4) == 0 && (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1 &&
-                       ctx->k1_impl != 2;
+    // ---- main path: one persistent CTA per scan, private L2-resident key slots ----
+    const bool sc_ok = vec16 && (cells % 4) == 0 && (((uintptr_t)out) & 15) == 0 &&
+                       (ctx->k1_impl == 0 ? n_scans >= ctx->sm_count / 2 : ctx->k1_impl == 3);
+    if (sc_ok) {
+        int ctas = ctx->sm_count;
+        if (ctas > n_scans) ctas = n_scans;
+        const size_t need = (size_t)ctx->sm_count * cells * 4;
+        if (need > ctx->keys_bytes) {
+            if (ctx->keys) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->keys); }
+            ctx->keys = nullptr;
+            ctx->keys_bytes = 0;
+            DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
+            ctx->keys_bytes = need;
+            DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
+        }
+        if ((rc = dsc_reserve_sync(ctx, 256))) return rc;
+        unsigned int *cursor = (unsigned int *)ctx->sync_buf;
+        DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, 16, st));
+        unsigned long long *stp = (unsigned long long *)stats;
+#define SC_LAUNCH2(F, V, H, U)                                                                                  \
+    k1_scan<F, V, H, U><<<ctas, SC_THREADS, 0, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, cursor, cfg)
+#define SC_LAUNCH(F, V, H)                                                                                      \
+    do {                                                                                                        \
+        if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3); else SC_LAUNCH2(F, V, H, 2);                              \
+    } while (0)
+        const bool full = p->full_height != 0;
+        if (cfg.fast_ok) {
+            if (p->variant == 0) { if (full) SC_LAUNCH(true, 0, true); else SC_LAUNCH(true, 0, false); }
+            else                 { if (full) SC_LAUNCH(true, 1, true); else SC_LAUNCH(true, 1, false); }
+        } else {
+            if (p->variant == 0) { if (full) SC_LAUNCH(false, 0, true); else SC_LAUNCH(false, 0, false); }
+            else                 { if (full) SC_LAUNCH(false, 1, true); else SC_LAUNCH(false, 1, false); }
+        }
+#undef SC_LAUNCH
+#undef SC_LAUNCH2
+        if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
+        if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
+        return DSC_OK;
+    }
+    // ---- tile path (small batches, huge scans): persistent tile kernel, shared L2-resident slot ring ----
+    const bool st_ok = vec16 && (cells % 4) == 0 && (((uintptr_t)out) & 15) == 0 && (ctx->k1_impl == 0 || ctx->k1_impl == 4);
     if (st_ok) {
         int n_slots = ctx->st_slots;
         if (n_slots > n_scans) n_slots = n_scans;

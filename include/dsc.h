@@ -89,7 +89,8 @@ const char *dsc_last_error(const dsc_ctx *ctx);
 int dsc_set_timing(dsc_ctx *ctx, int enabled);
 float dsc_last_kernel_ms(const dsc_ctx *ctx);
 /* Engine options (debugging / A-B measurements):
- *   "k1_impl"  0 = auto, 1 = force the L2-key-grid kernel, 2 = force the shared-memory half-grid kernel */
+ *   "k1_impl"  0 = auto, 1 = chunked L2-key kernels, 2 = shared-memory half-grid kernel,
+ *              3 = scan-per-CTA kernel, 4 = tile kernel;  plus kernel-shape knobs (see dsc_api.cu) */
 int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value);
 /* Number of engine kernels launched since the context was created. */
 int64_t dsc_kernel_launches(const dsc_ctx *ctx);

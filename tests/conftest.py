@@ -62,12 +62,12 @@ def orc():
     return oracle
 
 
-@pytest.fixture(scope="session", params=["stream", "l2keys", "halfgrid"])
+@pytest.fixture(scope="session", params=["auto", "l2keys", "halfgrid", "scan", "tile"])
 def engine(request):
     """One engine per K1 implementation: the default streaming kernel and the two A/B variants."""
     from distropointclouds_b200.engine import Engine
     e = Engine(0)
-    e.set_option("k1_impl", {"stream": 0, "l2keys": 1, "halfgrid": 2}[request.param])
+    e.set_option("k1_impl", {"auto": 0, "l2keys": 1, "halfgrid": 2, "scan": 3, "tile": 4}[request.param])
     yield e
     e.close()
 
