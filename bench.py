@@ -152,6 +152,9 @@ def run_ours(args):
         eng.set_option("pf_dist", args.pf_dist)
     eng.set_option("st_cfg", args.st_cfg)
     eng.set_option("sc_cfg", args.sc_cfg)
+    if args.l2_hints >= 0:
+        eng.set_option("l2_hints", args.l2_hints)
+    eng.set_option("l2_persist", args.l2_persist)
     if args.st_slots > 0:
         eng.set_option("st_slots", args.st_slots)
     params = ScanContextParams(R, S, MAXLEN)
@@ -269,6 +272,8 @@ def main():
     ap.add_argument("--points", type=int, default=120000, help="points per scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--l2-hints", type=int, default=-1, help="L2 eviction hints (A/B runs)")
+    ap.add_argument("--l2-persist", type=int, default=0, help="L2 persisting window for key slots (A/B runs)")
     ap.add_argument("--sc-cfg", type=int, default=0, help="scan kernel shape (A/B runs)")
     ap.add_argument("--st-cfg", type=int, default=0, help="streaming kernel shape (A/B runs)")
     ap.add_argument("--st-slots", type=int, default=0, help="key-grid slots of the streaming kernel (A/B runs)")

@@ -147,6 +147,32 @@ k1_build_keys(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offse
 // computed sector decides.  There is no traffic between the CTAs at all: reduction = local ATOMS.MAX,
 // write-out = one coalesced pass per scan that also re-zeroes the grid for the next scan.
 
+// L2 eviction policies: the point stream is read once (evict first); the key slots are the hot working
+// set that must stay resident between a scan's REDs and its decode (evict last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_stream_f4_hint(const void *p, uint64_t pol)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_max_global_hint(uint32_t *p, uint32_t v, uint64_t pol)
+{
+    asm volatile("red.relaxed.gpu.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
 // fire-and-forget reduction at L2: no return value, nothing for the warp to wait on
 __device__ __forceinline__ void red_max_global(uint32_t *p, uint32_t v)
 {
@@ -398,7 +424,7 @@ struct StreamSync {            // zeroed before every launch
 template <bool FAST, int VARIANT, bool FULL>
 __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v,
                                          uint32_t *__restrict__ grid, unsigned &n_clamped,
-                                         unsigned long long *__restrict__ stats, int scan)
+                                         unsigned long long *__restrict__ stats, int scan, uint64_t key_policy = 0)
 {
     int ring, sector;
     bool beyond, ok = false;
@@ -433,7 +459,8 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea,
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
     if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
-    red_max_global(grid + ring * cfg.S + sector, key);
+    if (key_policy) red_max_global_hint(grid + ring * cfg.S + sector, key, key_policy);
+    else red_max_global(grid + ring * cfg.S + sector, key);
 }
 
 // keys (L2) -> float grid (HBM, coalesced 128-bit streaming stores); re-zeroes the slot.  Out of line so
@@ -623,7 +650,7 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
 // HBM sees each point once and each output cell once.
 constexpr int SC_THREADS = 1024;
 
-template <bool FAST, int VARIANT, bool FULL, int U>
+template <bool FAST, int VARIANT, bool FULL, int U, int HINTS>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
@@ -636,6 +663,8 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int cells = cfg.R * cfg.S;
     const int nvec = cells >> 2;                 // host guarantees cells % 4 == 0
     uint32_t *grid = keys + (size_t)blockIdx.x * cells;
+    const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
+    const uint64_t pol_keys = HINTS == 2 ? l2_policy_evict_last() : 0;
     if (tid == 0) {
         fill_exact_args(&s_ea, cfg);
         s_next[0] = (int)atomicAdd(cursor, 1u);
@@ -655,29 +684,29 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
         float4 a[U], b[U];
         if (nfull > 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * SC_THREADS);
+            for (int u = 0; u < U; ++u) a[u] = (HINTS ? ld_stream_f4_hint(p + u * SC_THREADS, pol_stream) : ld_stream_f4(p + u * SC_THREADS));
         }
         int step = 0;
         while (step + 1 < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) b[u] = ld_stream_f4(p + STEP + u * SC_THREADS);
+            for (int u = 0; u < U; ++u) b[u] = (HINTS ? ld_stream_f4_hint(p + STEP + u * SC_THREADS, pol_stream) : ld_stream_f4(p + STEP + u * SC_THREADS));
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan);
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
             p += 2 * STEP;
             step += 2;
             if (step < nfull) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) a[u] = ld_stream_f4(p + u * SC_THREADS);
+                for (int u = 0; u < U; ++u) a[u] = (HINTS ? ld_stream_f4_hint(p + u * SC_THREADS, pol_stream) : ld_stream_f4(p + u * SC_THREADS));
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, b[u], grid, n_clamped, stats, scan);
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, b[u], grid, n_clamped, stats, scan, pol_keys);
         }
         if (step < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan);
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
         }
         for (int i = nfull * STEP + tid; i < n; i += SC_THREADS)              // ragged tail
-            st_point<FAST, VARIANT, FULL>(cfg, &s_ea, ld_stream_f4(s4 + i), grid, n_clamped, stats, scan);
+            st_point<FAST, VARIANT, FULL>(cfg, &s_ea, ld_stream_f4(s4 + i), grid, n_clamped, stats, scan, pol_keys);
         if (stats) {
             unsigned long long *st = stats + (int64_t)scan * 6;
             const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
@@ -899,14 +928,33 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
         }
         if ((rc = dsc_reserve_sync(ctx, 256))) return rc;
+        // optional: pin the key slots in L2 with a persisting access-policy window on the launch stream
+        cudaStreamAttrValue win;
+        memset(&win, 0, sizeof win);
+        if (ctx->l2_persist && ctx->persist_max > 0) {
+            if (!ctx->persist_set) {
+                const size_t lim = need < ctx->persist_max ? need : ctx->persist_max;
+                DSC_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim));
+                ctx->persist_set = lim;
+            }
+            win.accessPolicyWindow.base_ptr = ctx->keys;
+            win.accessPolicyWindow.num_bytes = need < ctx->window_max ? need : ctx->window_max;
+            const double ratio = (double)ctx->persist_set / (double)win.accessPolicyWindow.num_bytes;
+            win.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+            win.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            win.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
+        }
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
         DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, 16, st));
         unsigned long long *stp = (unsigned long long *)stats;
-#define SC_LAUNCH2(F, V, H, U)                                                                                  \
-    k1_scan<F, V, H, U><<<ctas, SC_THREADS, 0, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, cursor, cfg)
+#define SC_LAUNCH2(F, V, H, U, HN)                                                                              \
+    k1_scan<F, V, H, U, HN><<<ctas, SC_THREADS, 0, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, cursor, cfg)
 #define SC_LAUNCH(F, V, H)                                                                                      \
     do {                                                                                                        \
-        if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3); else SC_LAUNCH2(F, V, H, 2);                              \
+        if (ctx->l2_hints == 0) { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 0); else SC_LAUNCH2(F, V, H, 2, 0); } \
+        else if (ctx->l2_hints == 1) { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 1); else SC_LAUNCH2(F, V, H, 2, 1); } \
+        else { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 2); else SC_LAUNCH2(F, V, H, 2, 2); }             \
     } while (0)
         const bool full = p->full_height != 0;
         if (cfg.fast_ok) {
@@ -919,6 +967,10 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
 #undef SC_LAUNCH
 #undef SC_LAUNCH2
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
+        if (win.accessPolicyWindow.num_bytes) {      // leave the caller's stream as we found it
+            win.accessPolicyWindow.num_bytes = 0;
+            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
+        }
         if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
         return DSC_OK;
     }
