@@ -17,7 +17,8 @@ struct dsc_ctx {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
-    int l2_hints = 1;                // 0 none, 1 evict-first point stream, 2 + evict-last key slots
+    int no_defgrid = 0;              // 1: do not use the default-grid specialisation (A/B runs)
+    int l2_hints = 1;                // 0 none, 1 evict-first point stream
     size_t persist_max = 0, window_max = 0, persist_set = 0;   // L2 persistence limits of the device
     int l2_persist = 0;              // 1: put the key slots under an L2 persisting access-policy window
     int sc_cfg = 0;                  // scan kernel: 0 = 2 loads x 2 sets per thread, 1 = 3 x 2

@@ -421,7 +421,7 @@ struct StreamSync {            // zeroed before every launch
     // followed by: unsigned tiles_done[n_scans]; unsigned decoded[n_scans];
 };
 
-template <bool FAST, int VARIANT, bool FULL>
+template <bool FAST, int VARIANT, bool FULL, bool DEF = false>
 __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v,
                                          uint32_t *__restrict__ grid, unsigned &n_clamped,
                                          unsigned long long *__restrict__ stats, int scan, uint64_t key_policy = 0)
@@ -429,7 +429,7 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea,
     int ring, sector;
     bool beyond, ok = false;
     if constexpr (FAST) {
-        ok = dsc::screened_core(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
+        ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
         if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
     }
     float zv = FULL ? v.z : __fadd_rn(v.z, cfg.offset);
@@ -459,8 +459,8 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea,
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
     if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
-    if (key_policy) red_max_global_hint(grid + ring * cfg.S + sector, key, key_policy);
-    else red_max_global(grid + ring * cfg.S + sector, key);
+    if (key_policy) red_max_global_hint(grid + ring * (DEF ? dsc::defgrid::S : cfg.S) + sector, key, key_policy);
+    else red_max_global(grid + ring * (DEF ? dsc::defgrid::S : cfg.S) + sector, key);
 }
 
 // keys (L2) -> float grid (HBM, coalesced 128-bit streaming stores); re-zeroes the slot.  Out of line so
@@ -650,7 +650,7 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
 // HBM sees each point once and each output cell once.
 constexpr int SC_THREADS = 1024;
 
-template <bool FAST, int VARIANT, bool FULL, int U, int HINTS>
+template <bool FAST, int VARIANT, bool FULL, int U, int HINTS, bool DEF>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
@@ -664,7 +664,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int nvec = cells >> 2;                 // host guarantees cells % 4 == 0
     uint32_t *grid = keys + (size_t)blockIdx.x * cells;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
-    const uint64_t pol_keys = HINTS == 2 ? l2_policy_evict_last() : 0;
+    const uint64_t pol_keys = 0;
     if (tid == 0) {
         fill_exact_args(&s_ea, cfg);
         s_next[0] = (int)atomicAdd(cursor, 1u);
@@ -691,7 +691,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 #pragma unroll
             for (int u = 0; u < U; ++u) b[u] = (HINTS ? ld_stream_f4_hint(p + STEP + u * SC_THREADS, pol_stream) : ld_stream_f4(p + STEP + u * SC_THREADS));
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
             p += 2 * STEP;
             step += 2;
             if (step < nfull) {
@@ -699,14 +699,14 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
                 for (int u = 0; u < U; ++u) a[u] = (HINTS ? ld_stream_f4_hint(p + u * SC_THREADS, pol_stream) : ld_stream_f4(p + u * SC_THREADS));
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, b[u], grid, n_clamped, stats, scan, pol_keys);
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, b[u], grid, n_clamped, stats, scan, pol_keys);
         }
         if (step < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
+            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
         }
         for (int i = nfull * STEP + tid; i < n; i += SC_THREADS)              // ragged tail
-            st_point<FAST, VARIANT, FULL>(cfg, &s_ea, ld_stream_f4(s4 + i), grid, n_clamped, stats, scan, pol_keys);
+            st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, ld_stream_f4(s4 + i), grid, n_clamped, stats, scan, pol_keys);
         if (stats) {
             unsigned long long *st = stats + (int64_t)scan * 6;
             const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
@@ -948,14 +948,18 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
         DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, 16, st));
         unsigned long long *stp = (unsigned long long *)stats;
+#define SC_LAUNCH3(F, V, H, U, HN, D)                                                                           \
+    k1_scan<F, V, H, U, HN, D><<<ctas, SC_THREADS, 0, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, cursor, cfg)
 #define SC_LAUNCH2(F, V, H, U, HN)                                                                              \
-    k1_scan<F, V, H, U, HN><<<ctas, SC_THREADS, 0, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, cursor, cfg)
+    do {                                                                                                        \
+        if (F && defgrid) SC_LAUNCH3(F, V, H, U, HN, true); else SC_LAUNCH3(F, V, H, U, HN, false);             \
+    } while (0)
 #define SC_LAUNCH(F, V, H)                                                                                      \
     do {                                                                                                        \
         if (ctx->l2_hints == 0) { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 0); else SC_LAUNCH2(F, V, H, 2, 0); } \
-        else if (ctx->l2_hints == 1) { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 1); else SC_LAUNCH2(F, V, H, 2, 1); } \
-        else { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 2); else SC_LAUNCH2(F, V, H, 2, 2); }             \
+        else { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 1); else SC_LAUNCH2(F, V, H, 2, 1); }             \
     } while (0)
+        const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
         const bool full = p->full_height != 0;
         if (cfg.fast_ok) {
             if (p->variant == 0) { if (full) SC_LAUNCH(true, 0, true); else SC_LAUNCH(true, 0, false); }
@@ -966,6 +970,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         }
 #undef SC_LAUNCH
 #undef SC_LAUNCH2
+#undef SC_LAUNCH3
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
         if (win.accessPolicyWindow.num_bytes) {      // leave the caller's stream as we found it
             win.accessPolicyWindow.num_bytes = 0;

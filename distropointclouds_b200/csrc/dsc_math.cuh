@@ -365,8 +365,24 @@ DSC_HD float round_nearest(float a) { return nearbyintf(a); }
 // Core of the screen: true when (ring, sector, beyond) are certain; false sends the point to bin_exact.
 // No zero substitution is needed here: a zero coordinate makes u == 0 (or NaN), so the approximate
 // angle is an exact multiple of 90 degrees -- a sector boundary -- and the point screens itself out.
-DSC_HD bool screened_core(const BinCfg &c, float x, float y, float noise_r, float noise_t, int *ring,
-                          int *sector, bool *beyond)
+// DEF = true bakes the constants of the reference's default grid (160 rings x 720 sectors, i.e. 0.5-degree
+// sectors) into the instruction stream as immediates: no constant-bank loads in the streaming loop (an LDC
+// there shares the long scoreboard with the in-flight 128-bit point loads and stalls on them).  Only the
+// ring scale (8/m for max_length 20, 2/m for 80) stays a run-time value.  Same arithmetic, same values.
+namespace defgrid {
+constexpr double kScale = (180.0 / 3.14159265358979323846) * 2.0;   // radians -> half-degree sectors
+constexpr float c0 = (float)(0.9999993443489075 * kScale), c1 = (float)(-0.33329859375953674 * kScale),
+                c2 = (float)(0.19946566224098206 * kScale), c3 = (float)(-0.1390862911939621 * kScale),
+                c4 = (float)(0.09642194956541061 * kScale), c5 = (float)(-0.05591229721903801 * kScale),
+                c6 = (float)(0.0218629352748394 * kScale), c7 = (float)(-0.004054560791701078 * kScale);
+constexpr int R = 160, S = 720;
+constexpr float q90 = 180.0f, q180 = 360.0f, q360 = 720.0f, Rp1_f = 161.0f;
+constexpr float fast_dr = (float)(161 * 1.5e-6), fast_ds = (float)(5.0e-4 * 2.0);
+}  // namespace defgrid
+
+template <bool DEF>
+DSC_HD bool screened_core_t(const BinCfg &c, float x, float y, float noise_r, float noise_t, int *ring,
+                            int *sector, bool *beyond)
 {
     const float ax = fabsf(x), ay = fabsf(y);
     // ring coordinate: sqrt.approx.ftz flushes a subnormal s to 0 (-> boundary 0 -> exact path);
@@ -377,26 +393,42 @@ DSC_HD bool screened_core(const BinCfg &c, float x, float y, float noise_r, floa
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float u = mn * approx_rcp(mx, noise_t);
     const float w = u * u;
-    float p = ffma(w, c.atan_c[7], c.atan_c[6]);
-    p = ffma(w, p, c.atan_c[5]);
-    p = ffma(w, p, c.atan_c[4]);
-    p = ffma(w, p, c.atan_c[3]);
-    p = ffma(w, p, c.atan_c[2]);
-    p = ffma(w, p, c.atan_c[1]);
-    p = ffma(w, p, c.atan_c[0]);
+    float p = ffma(w, DEF ? defgrid::c7 : c.atan_c[7], DEF ? defgrid::c6 : c.atan_c[6]);
+    p = ffma(w, p, DEF ? defgrid::c5 : c.atan_c[5]);
+    p = ffma(w, p, DEF ? defgrid::c4 : c.atan_c[4]);
+    p = ffma(w, p, DEF ? defgrid::c3 : c.atan_c[3]);
+    p = ffma(w, p, DEF ? defgrid::c2 : c.atan_c[2]);
+    p = ffma(w, p, DEF ? defgrid::c1 : c.atan_c[1]);
+    p = ffma(w, p, DEF ? defgrid::c0 : c.atan_c[0]);
     float qs = p * u;
-    if (ay > ax) qs = c.q90 - qs;
-    if (x < 0.0f) qs = c.q180 - qs;
-    if (y < 0.0f) qs = c.q360 - qs;
+    if (ay > ax) qs = (DEF ? defgrid::q90 : c.q90) - qs;
+    if (x < 0.0f) qs = (DEF ? defgrid::q180 : c.q180) - qs;
+    if (y < 0.0f) qs = (DEF ? defgrid::q360 : c.q360) - qs;
     // distance to the nearest bin boundary (NaN compares false everywhere => not ok)
     const float dr = fabsf(qr - round_nearest(qr)), ds = fabsf(qs - round_nearest(qs));
-    const bool far_out = qr >= c.Rp1_f;                  // deep in the clamp / reject zone
-    const bool ok = (ds > c.fast_ds) && (far_out || dr > c.fast_dr) && (qr < INFINITY);
-    const int ir = (int)fminf(qr, c.Rp1_f);              // qr >= 0: truncation == floor; clamped so the cast is defined
-    *beyond = ir >= c.R;
-    *ring = min_i(ir, c.R - 1);
+    const float Rp1 = DEF ? defgrid::Rp1_f : c.Rp1_f;
+    const int Rr = DEF ? defgrid::R : c.R;
+    const bool far_out = qr >= Rp1;                      // deep in the clamp / reject zone
+    const bool ok = (ds > (DEF ? defgrid::fast_ds : c.fast_ds)) &&
+                    (far_out || dr > (DEF ? defgrid::fast_dr : c.fast_dr)) && (qr < INFINITY);
+    const int ir = (int)fminf(qr, Rp1);                  // qr >= 0: truncation == floor; clamped so the cast is defined
+    *beyond = ir >= Rr;
+    *ring = min_i(ir, Rr - 1);
     *sector = (int)qs;
     return ok;
+}
+
+static inline bool is_default_grid(const BinCfg &c)
+{
+    return c.fast_ok && c.R == defgrid::R && c.S == defgrid::S && c.atan_c[0] == defgrid::c0 &&
+           c.atan_c[7] == defgrid::c7 && c.q90 == defgrid::q90 && c.q360 == defgrid::q360 &&
+           c.Rp1_f == defgrid::Rp1_f && c.fast_dr == defgrid::fast_dr && c.fast_ds == defgrid::fast_ds;
+}
+
+DSC_HD bool screened_core(const BinCfg &c, float x, float y, float noise_r, float noise_t, int *ring,
+                          int *sector, bool *beyond)
+{
+    return screened_core_t<false>(c, x, y, noise_r, noise_t, ring, sector, beyond);
 }
 
 DSC_HD BinResult bin_screened(const BinCfg &c, float x, float y, float z, float noise_r, float noise_t,

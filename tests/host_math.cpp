@@ -37,6 +37,25 @@ void hm_bin_fast(int R, int S, double max_length, int variant, int full_height, 
 }
 #endif
 
+#ifdef DSC_HAVE_FAST
+// the compile-time-constant specialisation must agree with the run-time one, bit for bit
+long long hm_defgrid_mismatches(double max_length, const float *xyz, long long n, int stride_floats, const float *noise)
+{
+    const dsc::BinCfg c = dsc::make_bin_cfg(160, 720, max_length, 0, 1, 2.0f, 0, 0);
+    if (!dsc::is_default_grid(c)) return -1;
+    long long bad = 0;
+    for (long long i = 0; i < n; ++i) {
+        const float *p = xyz + i * stride_floats;
+        int r0, s0, r1, s1; bool b0, b1;
+        const float nr = noise ? noise[2 * i] : 0.f, nt = noise ? noise[2 * i + 1] : 0.f;
+        const bool k0 = dsc::screened_core_t<false>(c, p[0], p[1], nr, nt, &r0, &s0, &b0);
+        const bool k1 = dsc::screened_core_t<true>(c, p[0], p[1], nr, nt, &r1, &s1, &b1);
+        if (k0 != k1 || (k0 && (r0 != r1 || s0 != s1 || b0 != b1))) ++bad;
+    }
+    return bad;
+}
+#endif
+
 unsigned hm_float_to_key(float z) { return dsc::float_to_key(z); }
 float hm_key_to_float(unsigned k) { return dsc::key_to_float(k); }
 }

@@ -27,6 +27,8 @@ def hm():
                                C.c_longlong, C.c_int, ip, ip, fp]
     L.hm_bin_fast.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float, fp, C.c_longlong, C.c_int,
                               fp, ip, ip, ip]
+    L.hm_defgrid_mismatches.argtypes = [C.c_double, fp, C.c_longlong, C.c_int, fp]
+    L.hm_defgrid_mismatches.restype = C.c_longlong
     L.hm_atan2f.argtypes = [C.c_float, C.c_float]
     L.hm_atan2f.restype = C.c_float
     L.hm_float_to_key.argtypes = [C.c_float]
@@ -173,3 +175,14 @@ def test_fast_path_on_synthetic_and_adversarial_points(hm):
             bad, slow = _check_fast(hm, pts, var=var, noise_mode=nm)
             assert bad == 0
             assert slow > 0.5        # these points really are near boundaries: most must fall back
+
+
+def test_default_grid_specialisation_is_bit_identical(hm, golden_scans):
+    """screened_core_t<true> (constants baked in as immediates) == screened_core_t<false> (constant bank)."""
+    fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(4)
+    for pts in (golden_scans["000840"], adversarial_points(n=100000)):
+        pts = np.ascontiguousarray(pts, np.float32)
+        noise = rng.uniform(-1, 1, (len(pts), 2)).astype(np.float32)
+        for ml in (20.0, 80.0):
+            assert hm.hm_defgrid_mismatches(ml, pts.ctypes.data_as(fp), len(pts), 4, noise.ctypes.data_as(fp)) == 0
