@@ -156,6 +156,7 @@ def run_ours(args):
         eng.set_option("l2_hints", args.l2_hints)
     eng.set_option("l2_persist", args.l2_persist)
     eng.set_option("no_defgrid", args.no_defgrid)
+    eng.set_option("sc_smem_rows", args.sc_smem_rows)
     if args.st_slots > 0:
         eng.set_option("st_slots", args.st_slots)
     params = ScanContextParams(R, S, MAXLEN)
@@ -274,6 +275,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--l2-hints", type=int, default=-1, help="L2 eviction hints (A/B runs)")
+    ap.add_argument("--sc-smem-rows", type=int, default=-1, help="scan kernel: resident ring rows (A/B runs)")
     ap.add_argument("--no-defgrid", type=int, default=0, help="disable the default-grid specialisation (A/B runs)")
     ap.add_argument("--l2-persist", type=int, default=0, help="L2 persisting window for key slots (A/B runs)")
     ap.add_argument("--sc-cfg", type=int, default=0, help="scan kernel shape (A/B runs)")

@@ -76,6 +76,7 @@ extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return DSC_ERR_INVALID;
     if (!strcmp(name, "k1_impl") && value >= 0 && value <= 4) { ctx->k1_impl = (int)value; return DSC_OK; }
+    if (!strcmp(name, "sc_smem_rows") && value >= -1 && value <= 65536) { ctx->sc_smem_rows = (int)value; return DSC_OK; }
     if (!strcmp(name, "no_defgrid") && value >= 0 && value <= 1) { ctx->no_defgrid = (int)value; return DSC_OK; }
     if (!strcmp(name, "l2_hints") && value >= 0 && value <= 1) { ctx->l2_hints = (int)value; return DSC_OK; }
     if (!strcmp(name, "l2_persist") && value >= 0 && value <= 1) { ctx->l2_persist = (int)value; return DSC_OK; }

@@ -17,6 +17,7 @@ struct dsc_ctx {
     std::string err;
     int64_t launches = 0;
     int timing = 0;
+    int sc_smem_rows = -1;           // scan kernel: ring rows kept in shared memory (-1 = as many as fit, 0 = none)
     int no_defgrid = 0;              // 1: do not use the default-grid specialisation (A/B runs)
     int l2_hints = 1;                // 0 none, 1 evict-first point stream
     size_t persist_max = 0, window_max = 0, persist_set = 0;   // L2 persistence limits of the device

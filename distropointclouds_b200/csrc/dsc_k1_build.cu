@@ -421,10 +421,20 @@ struct StreamSync {            // zeroed before every launch
     // followed by: unsigned tiles_done[n_scans]; unsigned decoded[n_scans];
 };
 
-template <bool FAST, int VARIANT, bool FULL, bool DEF = false>
+// Hybrid placement of the key grid (scan kernel): `ns` ring rows live in shared memory -- rings
+// 0 .. ns-2 plus the clamp ring R-1, which together hold 70-90 % of the points of a KITTI-like scan --
+// and take the LDS pre-check + ATOMS.MAX path; the remaining rings go to the CTA's L2 slot with RED.MAX.
+struct SmemRows {
+    uint32_t base;   // shared-window address of the resident rows
+    int lim;         // cells below lim are resident rows 0 .. ns-2            (0 when nothing is resident)
+    int last;        // first cell of the clamp ring, kept in resident row ns-1 (INT_MAX when nothing is)
+};
+
+template <bool FAST, int VARIANT, bool FULL, bool DEF = false, bool SMEM = false>
 __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v,
                                          uint32_t *__restrict__ grid, unsigned &n_clamped,
-                                         unsigned long long *__restrict__ stats, int scan, uint64_t key_policy = 0)
+                                         unsigned long long *__restrict__ stats, int scan, uint64_t key_policy = 0,
+                                         const SmemRows sm = SmemRows{0u, 0, 0x7fffffff})
 {
     int ring, sector;
     bool beyond, ok = false;
@@ -459,8 +469,18 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea,
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
     if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
-    if (key_policy) red_max_global_hint(grid + ring * (DEF ? dsc::defgrid::S : cfg.S) + sector, key, key_policy);
-    else red_max_global(grid + ring * (DEF ? dsc::defgrid::S : cfg.S) + sector, key);
+    const int S = DEF ? dsc::defgrid::S : cfg.S;
+    const int cell = ring * S + sector;           // slow path: ring == 0 and sector already holds the cell
+    if constexpr (SMEM) {
+        if (cell < sm.lim || cell >= sm.last) {
+            const int local = cell < sm.lim ? cell : cell - sm.last + sm.lim;   // clamp ring -> row ns-1
+            const uint32_t addr = sm.base + (uint32_t)local * 4u;
+            if (key > lds_u32(addr)) reds_max_u32(addr, key);   // LDS pre-check: most points are not a new maximum
+            return;
+        }
+    }
+    if (key_policy) red_max_global_hint(grid + cell, key, key_policy);
+    else red_max_global(grid + cell, key);
 }
 
 // keys (L2) -> float grid (HBM, coalesced 128-bit streaming stores); re-zeroes the slot.  Out of line so
@@ -654,17 +674,23 @@ template <bool FAST, int VARIANT, bool FULL, int U, int HINTS, bool DEF>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
-        unsigned int *__restrict__ cursor, const BinCfg cfg)
+        unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg)
 {
     constexpr int STEP = SC_THREADS * U;
+    extern __shared__ __align__(16) uint32_t srows[];          // ns ring rows of keys
     __shared__ int s_next[2];
     __shared__ ExactArgs s_ea;
     const int tid = threadIdx.x;
-    const int cells = cfg.R * cfg.S;
-    const int nvec = cells >> 2;                 // host guarantees cells % 4 == 0
+    const int R = DEF ? dsc::defgrid::R : cfg.R, S = DEF ? dsc::defgrid::S : cfg.S;
+    const int cells = R * S;
+    const int rowvec = S >> 2;                   // host guarantees S % 4 == 0
     uint32_t *grid = keys + (size_t)blockIdx.x * cells;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
-    const uint64_t pol_keys = 0;
+    SmemRows sm;
+    sm.base = (uint32_t)__cvta_generic_to_shared(srows);
+    sm.lim = ns > 0 ? (ns - 1) * S : 0;
+    sm.last = ns > 0 ? (R - 1) * S : 0x7fffffff;
+    for (int i = tid; i < ns * rowvec; i += SC_THREADS) reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         fill_exact_args(&s_ea, cfg);
         s_next[0] = (int)atomicAdd(cursor, 1u);
@@ -682,31 +708,34 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
         const int nfull = n / STEP;
         const float4 *p = s4 + tid;
         float4 a[U], b[U];
+#define SC_LD(ptr) (HINTS ? ld_stream_f4_hint((ptr), pol_stream) : ld_stream_f4((ptr)))
+#define SC_PT(v) st_point<FAST, VARIANT, FULL, DEF, true>(cfg, &s_ea, (v), grid, n_clamped, stats, scan, 0, sm)
         if (nfull > 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = (HINTS ? ld_stream_f4_hint(p + u * SC_THREADS, pol_stream) : ld_stream_f4(p + u * SC_THREADS));
+            for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * SC_THREADS);
         }
         int step = 0;
         while (step + 1 < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) b[u] = (HINTS ? ld_stream_f4_hint(p + STEP + u * SC_THREADS, pol_stream) : ld_stream_f4(p + STEP + u * SC_THREADS));
+            for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * SC_THREADS);
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
+            for (int u = 0; u < U; ++u) SC_PT(a[u]);
             p += 2 * STEP;
             step += 2;
             if (step < nfull) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) a[u] = (HINTS ? ld_stream_f4_hint(p + u * SC_THREADS, pol_stream) : ld_stream_f4(p + u * SC_THREADS));
+                for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * SC_THREADS);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, b[u], grid, n_clamped, stats, scan, pol_keys);
+            for (int u = 0; u < U; ++u) SC_PT(b[u]);
         }
         if (step < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, a[u], grid, n_clamped, stats, scan, pol_keys);
+            for (int u = 0; u < U; ++u) SC_PT(a[u]);
         }
-        for (int i = nfull * STEP + tid; i < n; i += SC_THREADS)              // ragged tail
-            st_point<FAST, VARIANT, FULL, DEF>(cfg, &s_ea, ld_stream_f4(s4 + i), grid, n_clamped, stats, scan, pol_keys);
+        for (int i = nfull * STEP + tid; i < n; i += SC_THREADS) SC_PT(SC_LD(s4 + i));   // ragged tail
+#undef SC_LD
+#undef SC_PT
         if (stats) {
             unsigned long long *st = stats + (int64_t)scan * 6;
             const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
@@ -714,24 +743,39 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             if (tid == 0) atomicAdd(st + 0, (unsigned long long)n);
         }
         __threadfence();                         // our REDs are performed ...
-        __syncthreads();                         // ... before any thread of the CTA reads the slot back
-        // ---- decode: keys (L2) -> floats (HBM), re-zero the slot ----
-        {
+        __syncthreads();                         // ... before any thread of the CTA reads the keys back
+        // ---- decode: keys -> floats (coalesced 128-bit streaming stores), re-zero ----
+        float4 *oq = reinterpret_cast<float4 *>(out + (size_t)scan * cells);
+        {   // resident rows: rings 0 .. ns-2 and the clamp ring R-1
+            const int nres = ns * rowvec;
+            const int lim = (ns - 1) * rowvec, shift = (R - ns) * rowvec;    // row ns-1 -> ring R-1
+            for (int i = tid; i < nres; i += SC_THREADS) {
+                const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
+                reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+                float4 f;
+                f.x = dsc::key_to_float(q.x);
+                f.y = dsc::key_to_float(q.y);
+                f.z = dsc::key_to_float(q.z);
+                f.w = dsc::key_to_float(q.w);
+                __stcs(oq + (i < lim ? i : i + shift), f);
+            }
+        }
+        if (ns < R) {   // L2 rows: rings ns-1 .. R-2
             const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
             uint4 *kz = reinterpret_cast<uint4 *>(grid);
-            float4 *oq = reinterpret_cast<float4 *>(out + (size_t)scan * cells);
+            const int lo = (ns > 0 ? ns - 1 : 0) * rowvec, hi = (ns > 0 ? R - 1 : R) * rowvec;
             constexpr int DU = 4;
-            for (int i0 = tid; i0 < nvec; i0 += SC_THREADS * DU) {
+            for (int i0 = lo + tid; i0 < hi; i0 += SC_THREADS * DU) {
                 uint4 q[DU];
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
                     const int i = i0 + d * SC_THREADS;
-                    if (i < nvec) q[d] = __ldcg(kq + i);
+                    if (i < hi) q[d] = __ldcg(kq + i);
                 }
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
                     const int i = i0 + d * SC_THREADS;
-                    if (i < nvec) {
+                    if (i < hi) {
                         float4 f;
                         f.x = dsc::key_to_float(q[d].x);
                         f.y = dsc::key_to_float(q[d].y);
@@ -913,7 +957,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     int rc;
     if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
     // ---- main path: one persistent CTA per scan, private L2-resident key slots ----
-    const bool sc_ok = vec16 && (cells % 4) == 0 && (((uintptr_t)out) & 15) == 0 &&
+    const bool sc_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0 &&
                        (ctx->k1_impl == 0 ? n_scans >= ctx->sm_count / 2 : ctx->k1_impl == 3);
     if (sc_ok) {
         int ctas = ctx->sm_count;
@@ -948,8 +992,19 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
         DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, 16, st));
         unsigned long long *stp = (unsigned long long *)stats;
+        // resident ring rows: as many as fit next to the static shared data (80 of 160 for S = 720)
+        int ns = (int)((ctx->smem_optin - 1024) / ((size_t)p->num_sector * 4));
+        if (ns > p->num_ring) ns = p->num_ring;
+        if (ns < 2 || ctx->sc_smem_rows == 0) ns = 0;
+        else if (ctx->sc_smem_rows > 0 && ctx->sc_smem_rows < ns) ns = ctx->sc_smem_rows < 2 ? 0 : ctx->sc_smem_rows;
+        const size_t sc_smem = (size_t)ns * p->num_sector * 4;
 #define SC_LAUNCH3(F, V, H, U, HN, D)                                                                           \
-    k1_scan<F, V, H, U, HN, D><<<ctas, SC_THREADS, 0, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, cursor, cfg)
+    do {                                                                                                        \
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, HN, D>,                                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
+        k1_scan<F, V, H, U, HN, D><<<ctas, SC_THREADS, sc_smem, st>>>(pts, d_offsets, n_scans, ctx->keys, out,  \
+                                                                      stp, cursor, ns, cfg);                    \
+    } while (0)
 #define SC_LAUNCH2(F, V, H, U, HN)                                                                              \
     do {                                                                                                        \
         if (F && defgrid) SC_LAUNCH3(F, V, H, U, HN, true); else SC_LAUNCH3(F, V, H, U, HN, false);             \
