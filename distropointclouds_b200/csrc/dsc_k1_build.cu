@@ -992,11 +992,15 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
         DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, 16, st));
         unsigned long long *stp = (unsigned long long *)stats;
-        // resident ring rows: as many as fit next to the static shared data (80 of 160 for S = 720)
-        int ns = (int)((ctx->smem_optin - 1024) / ((size_t)p->num_sector * 4));
+        // resident ring rows.  Shared memory and L1 share 256 KB per SM and the 128-bit streaming loads
+        // land in L1: with the grid rows taking the full 227 KB the kernel loses 20 % (measured sweep in
+        // profiles/r1_notes.md), so stay inside the 164 KB carve-out step: 56 of 160 rows for S = 720.
+        const size_t sc_budget = (size_t)164 * 1024 - 1024 - 256;
+        int ns = (int)((sc_budget < ctx->smem_optin ? sc_budget : ctx->smem_optin - 1024) / ((size_t)p->num_sector * 4));
+        if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                     // A/B override
+        if ((size_t)ns * p->num_sector * 4 + 1024 > ctx->smem_optin) ns = (int)((ctx->smem_optin - 1024) / ((size_t)p->num_sector * 4));
         if (ns > p->num_ring) ns = p->num_ring;
-        if (ns < 2 || ctx->sc_smem_rows == 0) ns = 0;
-        else if (ctx->sc_smem_rows > 0 && ctx->sc_smem_rows < ns) ns = ctx->sc_smem_rows < 2 ? 0 : ctx->sc_smem_rows;
+        if (ns < 2) ns = 0;
         const size_t sc_smem = (size_t)ns * p->num_sector * 4;
 #define SC_LAUNCH3(F, V, H, U, HN, D)                                                                           \
     do {                                                                                                        \
