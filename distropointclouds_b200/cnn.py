@@ -1,0 +1,143 @@
+"""Config 4: scan contexts born on the GPU -> K4 (to_tensor01) -> the reference's TinyCNN -> masks.
+
+The network itself is the reference's (distro_model/tiny_sc_ped.py:134-154, weights
+``tinycnn_best.pth``) and stays a stock PyTorch/cuDNN module -- PyTorch is plumbing here, the
+engine's job is to hand it device-resident, already normalised grids so that the host round trip of
+``run_inference`` (tiny_sc_ped.py:217-234: np.load -> to_tensor01 -> .to(device)) disappears.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .engine import Engine, ScanContextParams, default_engine, pack_scans
+
+# (kind, in, out) per layer of tiny_sc_ped.TinyCNN; 'P' = MaxPool2d(2).  Index positions inside the two
+# nn.Sequential containers match the reference so that its state_dict loads with strict=True.
+_ENC = (("c3", 1, 16), ("c3", 16, 32), ("P",), ("c3", 32, 64), ("P",), ("c3", 64, 128), ("P",))
+_DEC = (("t2", 128, 64), ("t2", 64, 32), ("t2", 32, 16), ("c1", 16, 1))
+
+
+def build_tiny_cnn(in_ch: int = 1):
+    """An nn.Module with the parameter names/shapes of tiny_sc_ped.TinyCNN (enc.*, dec.*)."""
+    import torch.nn as nn
+
+    def stack(spec, first_in):
+        mods = []
+        for item in spec:
+            if item[0] == "P":
+                mods.append(nn.MaxPool2d(2))
+                continue
+            kind, cin, cout = item
+            cin = first_in if (first_in is not None and not mods) else cin
+            if kind == "c3":
+                mods += [nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True)]
+            elif kind == "t2":
+                mods += [nn.ConvTranspose2d(cin, cout, 2, stride=2), nn.BatchNorm2d(cout), nn.ReLU(inplace=True)]
+            else:
+                mods.append(nn.Conv2d(cin, cout, 1))
+        return nn.Sequential(*mods)
+
+    class TinyCNN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc = stack(_ENC, in_ch)
+            self.dec = stack(_DEC, None)
+
+        def forward(self, x):
+            return self.dec(self.enc(x))
+
+    return TinyCNN()
+
+
+class ScanContextCnnPipeline:
+    """points (device or host) -> grids -> normalised grids -> logits -> probabilities/masks, all on one GPU.
+
+    precision: "fp32" (cuDNN fp32, TF32 off: the parity mode), "tf32" (PyTorch's default for convolutions)
+    or "bf16" (autocast).  Parity is defined on fp32 logits; the faster modes are opt-in.
+    """
+
+    def __init__(self, weights_path: Optional[str] = None, device: int = 0, precision: str = "fp32",
+                 engine: Optional[Engine] = None, chunk: int = 64, model=None):
+        import torch
+        if precision not in ("fp32", "tf32", "bf16"):
+            raise ValueError("precision must be fp32, tf32 or bf16")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.engine = engine if engine is not None else default_engine(device)
+        self.precision = precision
+        self.chunk = int(chunk)
+        self.model = model if model is not None else build_tiny_cnn()
+        if weights_path is not None:
+            sd = torch.load(weights_path, map_location="cpu", weights_only=True)      # tiny_sc_ped.py:221
+            self.model.load_state_dict(sd, strict=True)
+        self.model = self.model.to(self.device).eval().to(memory_format=torch.channels_last)
+        self._norm = None
+
+    # -- stages ------------------------------------------------------------------------------------
+    def build_grids(self, pts, offsets: np.ndarray, params: ScanContextParams, want_norm: bool = True,
+                    stride_bytes: int = 16):
+        """K1 (+K4) on a device-resident packed point tensor.  Returns (grids, norm|None) CUDA tensors."""
+        torch = self.torch
+        n = len(offsets) - 1
+        grids = torch.empty((n, params.num_ring, params.num_sector), dtype=torch.float32, device=self.device)
+        norm = torch.empty_like(grids) if want_norm else None
+        self.engine.build_device(pts, offsets, params, grids, norm, None, stride_bytes)
+        return grids, norm
+
+    def logits_from_norm(self, norm):
+        """norm: (n,R,S) float32 CUDA tensor in [0,1] -> (n,R,S) float32 logits."""
+        torch = self.torch
+        out = torch.empty_like(norm)
+        tf32 = self.precision != "fp32"
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            with torch.no_grad():
+                for a in range(0, norm.shape[0], self.chunk):
+                    x = norm[a:a + self.chunk].unsqueeze(1).contiguous(memory_format=torch.channels_last)
+                    if self.precision == "bf16":
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            y = self.model(x)
+                    else:
+                        y = self.model(x)
+                    out[a:a + self.chunk] = y[:, 0].float()
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        return out
+
+    # -- whole pipeline ----------------------------------------------------------------------------
+    def infer_device(self, pts, offsets: np.ndarray, params: ScanContextParams = ScanContextParams(),
+                     thr: float = 0.5, stride_bytes: int = 16):
+        """Returns (grids, logits, mask uint8) as CUDA tensors; nothing touches the host."""
+        grids, norm = self.build_grids(pts, offsets, params, True, stride_bytes)
+        logits = self.logits_from_norm(norm)
+        mask = (self.torch.sigmoid(logits) > thr).to(self.torch.uint8)                 # tiny_sc_ped.py:227-228
+        return grids, logits, mask
+
+    def infer_scans(self, scans: Sequence[np.ndarray], params: ScanContextParams = ScanContextParams(),
+                    thr: float = 0.5):
+        """Host scans (list of (N,3|4) float32) -> (grids, probs, masks) NumPy arrays, like run_inference
+        (tiny_sc_ped.py:217-234) for a batch."""
+        torch = self.torch
+        pts, offsets, stride = pack_scans(list(scans))
+        d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to(self.device)
+        grids, logits, mask = self.infer_device(d_pts, offsets, params, thr, stride)
+        return grids.cpu().numpy(), torch.sigmoid(logits).cpu().numpy(), mask.cpu().numpy()
+
+
+def mask_to_detections(mask: np.ndarray, min_pixels: int = 20):
+    """tiny_sc_ped.py:196-215: connected components of the binary mask -> centre cells (host, scipy)."""
+    from scipy import ndimage as ndi
+    lab, n = ndi.label(np.asarray(mask) > 0)
+    dets = []
+    for i in range(1, n + 1):
+        coords = np.argwhere(lab == i)
+        if coords.shape[0] < min_pixels:
+            continue
+        r_mean, s_mean = coords[:, 0].mean(), coords[:, 1].mean()
+        dets.append({"center_ring_idx": float(r_mean), "center_sector_idx": float(s_mean),
+                     "area_pixels": int(coords.shape[0])})
+    return dets

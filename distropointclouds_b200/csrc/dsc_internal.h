@@ -19,10 +19,10 @@ struct dsc_ctx {
     int timing = 0;
     int sc_smem_rows = -1;           // scan kernel: ring rows kept in shared memory (-1 = as many as fit, 0 = none)
     int no_defgrid = 0;              // 1: do not use the default-grid specialisation (A/B runs)
-    int l2_hints = 1;                // 0 none, 1 evict-first point stream
-    size_t persist_max = 0, window_max = 0, persist_set = 0;   // L2 persistence limits of the device
-    int l2_persist = 0;              // 1: put the key slots under an L2 persisting access-policy window
     int sc_cfg = 0;                  // scan kernel: 0 = 2 loads x 2 sets per thread, 1 = 3 x 2
+    int sc_loader = 0;               // scan kernel point loader: 0 = 128-bit register loads, 1-4 = TMA ring shapes (k1_ring)
+    int sc_split = -1;               // scan kernel: -1 auto, 0 never split scans into items, 1 always
+    int sc_item_points = 131072;     // scan kernel: target points per work item when scans are split
     int st_cfg = 0;                  // streaming kernel shape: 0 = 8 pts/thread, 3 CTAs/SM; 1 = 6 pts/thread, 4 CTAs/SM
     int st_slots = 64;               // key-grid slots of the streaming kernel (L2-resident ring)
     void *sync_buf = nullptr;        // streaming kernel: cursor, per-scan counters, tile table

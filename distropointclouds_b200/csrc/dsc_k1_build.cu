@@ -670,21 +670,164 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
 // HBM sees each point once and each output cell once.
 constexpr int SC_THREADS = 1024;
 
-template <bool FAST, int VARIANT, bool FULL, int U, int HINTS, bool DEF>
+// SPLIT = true: a scan is cut into `parts` contiguous point ranges (work items) that different CTAs
+// process concurrently -- for multi-million-point scans and for batches with fewer scans than SMs, where
+// one CTA per scan would leave most of the chip idle.  The scan's own output grid doubles as its key
+// grid (zeroed by the host before the launch): L2 rows take RED.MAX straight into it, the resident rows
+// are folded into it with RED.MAX when the item ends, and the CTA that retires the scan's last item
+// decodes the keys to floats in place.  The grid of a scan in flight is 460 KB and stays in L2.
+struct SplitArgs {
+    const int64_t *item_base;    // [n_scans + 1] first item of each scan (ragged batches), or nullptr
+    unsigned int *done;          // [n_scans] items retired per scan (zeroed before the launch)
+    int total_items;
+    int parts_uniform;           // > 0: every scan has this many items
+};
+
+// work item -> (scan, first point, point count, parts of the scan, key grid)
+template <bool SPLIT>
+__device__ __forceinline__ void sc_item(int item, const int64_t *__restrict__ offsets, int n_scans, const SplitArgs &sp,
+                                        int &scan, int &parts, int64_t &p0, int &n)
+{
+    scan = item;
+    parts = 1;
+    if constexpr (SPLIT) {
+        int part;
+        st_locate(item, sp.item_base, n_scans, sp.parts_uniform, scan, part);
+        parts = sp.parts_uniform > 0 ? sp.parts_uniform : (int)(sp.item_base[scan + 1] - sp.item_base[scan]);
+        const int64_t q0 = offsets[scan];
+        const int64_t nn = offsets[scan + 1] - q0;
+        const int64_t chunk = (nn + parts - 1) / parts;
+        const int64_t start = (int64_t)part * chunk;
+        p0 = q0 + (start < nn ? start : nn);
+        n = (int)(start < nn ? (nn - start < chunk ? nn - start : chunk) : 0);
+    } else {
+        p0 = offsets[scan];
+        n = (int)(offsets[scan + 1] - p0);       // host guarantees < 2^31 points per scan
+    }
+}
+
+// End of a work item.  Non-split: this CTA owns the whole scan -- decode the resident rows and the private
+// L2 slot to floats (coalesced 128-bit streaming stores) and re-zero both.  Split: fold the resident rows
+// into the scan's key grid (== its output grid), count the item as retired, and if it was the scan's last
+// item decode the grid in place.  Ends with a CTA barrier in both cases.
+template <bool SPLIT>
+__device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid,
+                                               float *__restrict__ out_scan, int ns, int R, int S, int scan, int parts,
+                                               unsigned int *__restrict__ done, int *s_last)
+{
+    const int tid = threadIdx.x;
+    const int rowvec = S >> 2;
+    const int cells = R * S;
+    const int nres = ns * rowvec;
+    const int lim = (ns - 1) * rowvec, shift = (R - ns) * rowvec;    // resident row ns-1 holds ring R-1
+    if constexpr (SPLIT) {
+        __syncthreads();                         // every shared-memory atomic of the item has landed
+        for (int i = tid; i < nres; i += SC_THREADS) {
+            const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
+            if ((q.x | q.y | q.z | q.w) == 0u) continue;
+            reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+            uint32_t *g = grid + 4 * (size_t)(i < lim ? i : i + shift);
+            if (q.x) red_max_global(g + 0, q.x);
+            if (q.y) red_max_global(g + 1, q.y);
+            if (q.z) red_max_global(g + 2, q.z);
+            if (q.w) red_max_global(g + 3, q.w);
+        }
+        __threadfence();                         // release: this CTA's REDs are performed ...
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(done + scan, 1u);          // ... before the item counts as retired
+            *s_last = prev + 1u == (unsigned)parts;
+            if (prev + 1u == (unsigned)parts) __threadfence();         // acquire: the other CTAs' REDs are visible
+        }
+        __syncthreads();
+        if (*s_last) {
+            uint4 *kq = reinterpret_cast<uint4 *>(grid);
+            const int nvec = cells >> 2;
+            constexpr int DU = 4;
+            for (int i0 = tid; i0 < nvec; i0 += SC_THREADS * DU) {
+                uint4 q[DU];
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int i = i0 + d * SC_THREADS;
+                    if (i < nvec) q[d] = __ldcg(kq + i);
+                }
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int i = i0 + d * SC_THREADS;
+                    if (i < nvec) {
+                        float4 f;
+                        f.x = dsc::key_to_float(q[d].x);
+                        f.y = dsc::key_to_float(q[d].y);
+                        f.z = dsc::key_to_float(q[d].z);
+                        f.w = dsc::key_to_float(q[d].w);
+                        __stcs(reinterpret_cast<float4 *>(kq) + i, f);
+                    }
+                }
+            }
+        }
+        __syncthreads();                         // s_last is rewritten by the next item
+    } else {
+        __threadfence();                         // our REDs are performed ...
+        __syncthreads();                         // ... before any thread of the CTA reads the keys back
+        float4 *oq = reinterpret_cast<float4 *>(out_scan);
+        for (int i = tid; i < nres; i += SC_THREADS) {       // resident rows: rings 0 .. ns-2 and the clamp ring
+            const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
+            reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+            float4 f;
+            f.x = dsc::key_to_float(q.x);
+            f.y = dsc::key_to_float(q.y);
+            f.z = dsc::key_to_float(q.z);
+            f.w = dsc::key_to_float(q.w);
+            __stcs(oq + (i < lim ? i : i + shift), f);
+        }
+        if (ns < R) {                            // L2 rows: rings ns-1 .. R-2
+            const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
+            uint4 *kz = reinterpret_cast<uint4 *>(grid);
+            const int lo = (ns > 0 ? ns - 1 : 0) * rowvec, hi = (ns > 0 ? R - 1 : R) * rowvec;
+            constexpr int DU = 4;
+            for (int i0 = lo + tid; i0 < hi; i0 += SC_THREADS * DU) {
+                uint4 q[DU];
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int i = i0 + d * SC_THREADS;
+                    if (i < hi) q[d] = __ldcg(kq + i);
+                }
+#pragma unroll
+                for (int d = 0; d < DU; ++d) {
+                    const int i = i0 + d * SC_THREADS;
+                    if (i < hi) {
+                        float4 f;
+                        f.x = dsc::key_to_float(q[d].x);
+                        f.y = dsc::key_to_float(q[d].y);
+                        f.z = dsc::key_to_float(q[d].z);
+                        f.w = dsc::key_to_float(q[d].w);
+                        __stcs(oq + i, f);
+                        __stcg(kz + i, make_uint4(0, 0, 0, 0));
+                    }
+                }
+            }
+        }
+        __threadfence();                         // the zeroes are performed ...
+        __syncthreads();                         // ... before the next scan's REDs
+    }
+}
+
+template <bool FAST, int VARIANT, bool FULL, int U, int HINTS, bool DEF, bool SPLIT>
 __global__ void __launch_bounds__(SC_THREADS, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
-        unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg)
+        unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg, const SplitArgs sp)
 {
     constexpr int STEP = SC_THREADS * U;
     extern __shared__ __align__(16) uint32_t srows[];          // ns ring rows of keys
     __shared__ int s_next[2];
+    __shared__ int s_last;
     __shared__ ExactArgs s_ea;
     const int tid = threadIdx.x;
     const int R = DEF ? dsc::defgrid::R : cfg.R, S = DEF ? dsc::defgrid::S : cfg.S;
     const int cells = R * S;
     const int rowvec = S >> 2;                   // host guarantees S % 4 == 0
-    uint32_t *grid = keys + (size_t)blockIdx.x * cells;
+    uint32_t *grid = SPLIT ? nullptr : keys + (size_t)blockIdx.x * cells;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
     SmemRows sm;
     sm.base = (uint32_t)__cvta_generic_to_shared(srows);
@@ -696,13 +839,16 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
         s_next[0] = (int)atomicAdd(cursor, 1u);
     }
     __syncthreads();
-    int scan = s_next[0];
+    const int n_items = SPLIT ? sp.total_items : n_scans;
+    int item = s_next[0];
     int par = 0;
-    while (scan < n_scans) {
-        // scan index after this one: fetched now, consumed after the scan (the round trip is hidden)
+    while (item < n_items) {
+        // work item after this one: fetched now, consumed after the item (the round trip is hidden)
         if (tid == 0) s_next[par ^ 1] = (int)atomicAdd(cursor, 1u);
-        const int64_t p0 = offsets[scan];
-        const int n = (int)(offsets[scan + 1] - p0);          // host guarantees < 2^31 points per scan
+        int scan, parts, n;
+        int64_t p0;
+        sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
+        if constexpr (SPLIT) grid = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
         const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         unsigned n_clamped = 0;
         const int nfull = n / STEP;
@@ -740,57 +886,163 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             unsigned long long *st = stats + (int64_t)scan * 6;
             const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
             if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
-            if (tid == 0) atomicAdd(st + 0, (unsigned long long)n);
+            if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
         }
-        __threadfence();                         // our REDs are performed ...
-        __syncthreads();                         // ... before any thread of the CTA reads the keys back
-        // ---- decode: keys -> floats (coalesced 128-bit streaming stores), re-zero ----
-        float4 *oq = reinterpret_cast<float4 *>(out + (size_t)scan * cells);
-        {   // resident rows: rings 0 .. ns-2 and the clamp ring R-1
-            const int nres = ns * rowvec;
-            const int lim = (ns - 1) * rowvec, shift = (R - ns) * rowvec;    // row ns-1 -> ring R-1
-            for (int i = tid; i < nres; i += SC_THREADS) {
-                const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
-                reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
-                float4 f;
-                f.x = dsc::key_to_float(q.x);
-                f.y = dsc::key_to_float(q.y);
-                f.z = dsc::key_to_float(q.z);
-                f.w = dsc::key_to_float(q.w);
-                __stcs(oq + (i < lim ? i : i + shift), f);
-            }
-        }
-        if (ns < R) {   // L2 rows: rings ns-1 .. R-2
-            const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
-            uint4 *kz = reinterpret_cast<uint4 *>(grid);
-            const int lo = (ns > 0 ? ns - 1 : 0) * rowvec, hi = (ns > 0 ? R - 1 : R) * rowvec;
-            constexpr int DU = 4;
-            for (int i0 = lo + tid; i0 < hi; i0 += SC_THREADS * DU) {
-                uint4 q[DU];
-#pragma unroll
-                for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * SC_THREADS;
-                    if (i < hi) q[d] = __ldcg(kq + i);
-                }
-#pragma unroll
-                for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * SC_THREADS;
-                    if (i < hi) {
-                        float4 f;
-                        f.x = dsc::key_to_float(q[d].x);
-                        f.y = dsc::key_to_float(q[d].y);
-                        f.z = dsc::key_to_float(q[d].z);
-                        f.w = dsc::key_to_float(q[d].w);
-                        __stcs(oq + i, f);
-                        __stcg(kz + i, make_uint4(0, 0, 0, 0));
-                    }
-                }
-            }
-        }
-        __threadfence();                         // the zeroes are performed ...
-        __syncthreads();                         // ... before the next scan's REDs (also publishes s_next)
+        sc_finish_item<SPLIT>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
         par ^= 1;
-        scan = s_next[par];
+        item = s_next[par];                      // published by the barriers of sc_finish_item
+    }
+}
+
+// ---- K1 main path, TMA flavour: the point stream is staged by the copy engine -----------------------------
+// Same work items, key-grid placement and write-out as k1_scan; the difference is the point loader.  One
+// elected thread keeps a ring of NST tiles (1024*U points, 16 KB * U each) in flight with cp.async.bulk
+// (global -> shared, completion on an mbarrier, L2 evict-first), so the bytes in flight per SM do not depend
+// on how the warps are scheduled and cost no registers; every thread then reads its own point with one
+// conflict-free LDS.128.  The ring runs ahead across item boundaries: the first tiles of the next item are
+// requested before the current item is decoded, so the decode overlaps the loads.  The loads bypass L1, which
+// frees the whole 227 KB of shared memory for grid rows + ring.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <bool FAST, int VARIANT, bool FULL, int U, int NST, bool DEF, bool SPLIT>
+__global__ void __launch_bounds__(SC_THREADS, 1)
+k1_ring(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
+        uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
+        unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg, const SplitArgs sp)
+{
+    constexpr int TILE = SC_THREADS * U;                       // points per tile
+    constexpr uint32_t TILE_BYTES = TILE * 16u;
+    extern __shared__ __align__(128) uint32_t srows[];         // [ns ring rows of keys][NST tiles]
+    __shared__ __align__(8) unsigned long long s_bar[2 * NST];  // full[NST], empty[NST]
+    __shared__ int s_next[2];
+    __shared__ int s_last;
+    __shared__ ExactArgs s_ea;
+    const int tid = threadIdx.x;
+    const int R = DEF ? dsc::defgrid::R : cfg.R, S = DEF ? dsc::defgrid::S : cfg.S;
+    const int cells = R * S;
+    const int rowvec = S >> 2;
+    uint32_t *grid = SPLIT ? nullptr : keys + (size_t)blockIdx.x * cells;
+    const uint64_t pol_stream = l2_policy_evict_first();
+    SmemRows sm;
+    sm.base = (uint32_t)__cvta_generic_to_shared(srows);
+    sm.lim = ns > 0 ? (ns - 1) * S : 0;
+    sm.last = ns > 0 ? (R - 1) * S : 0x7fffffff;
+    const uint32_t ring = sm.base + (((uint32_t)ns * (uint32_t)S * 4u + 127u) & ~127u);
+    const uint32_t bar_full = (uint32_t)__cvta_generic_to_shared(s_bar), bar_empty = bar_full + 8u * NST;
+    for (int i = tid; i < ns * rowvec; i += SC_THREADS) reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+    const int n_items = SPLIT ? sp.total_items : n_scans;
+
+    // producer state (thread 0 only): g_prod = tiles requested so far; tile g lives in stage g % NST, its
+    // `full` phase is (g / NST) & 1 and it may be requested once tile g - NST has been released
+    auto request = [&](unsigned g, const uint8_t *src, uint32_t bytes) {
+        const unsigned s = g % NST;
+        if (g >= (unsigned)NST) mbar_wait(bar_empty + 8u * s, ((g / NST) - 1u) & 1u);
+        mbar_expect_tx(bar_full + 8u * s, bytes);
+        bulk_load(ring + s * TILE_BYTES, src, bytes, bar_full + 8u * s, pol_stream);
+    };
+    // first tiles of an item (at most NST), requested ahead of time; g0 = global index of its tile 0
+    auto prologue = [&](int item_, unsigned g0) {
+        if (item_ >= n_items) return;
+        int scan_, parts_, n_;
+        int64_t p0_;
+        sc_item<SPLIT>(item_, offsets, n_scans, sp, scan_, parts_, p0_, n_);
+        const uint8_t *src = pts + p0_ * 16;
+        const int nt_ = (n_ + TILE - 1) / TILE;
+        for (int k = 0; k < NST && k < nt_; ++k) {
+            const int cnt = min(TILE, n_ - k * TILE);
+            request(g0 + (unsigned)k, src + (size_t)k * TILE_BYTES, (uint32_t)cnt * 16u);
+        }
+    };
+
+    if (tid == 0) {
+        fill_exact_args(&s_ea, cfg);
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(bar_full + 8u * i, 1u);
+            mbar_init(bar_empty + 8u * i, SC_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_next[0] = (int)atomicAdd(cursor, 1u);
+    }
+    __syncthreads();
+    int item = s_next[0];
+    int par = 0;
+    unsigned g = 0;                              // global tile counter of this CTA (same in every thread)
+    if (tid == 0) prologue(item, 0u);
+    while (item < n_items) {
+        if (tid == 0) s_next[par ^ 1] = (int)atomicAdd(cursor, 1u);
+        int scan, parts, n;
+        int64_t p0;
+        sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
+        if constexpr (SPLIT) grid = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
+        const uint8_t *src = pts + p0 * 16;
+        const int nt = (n + TILE - 1) / TILE;
+        unsigned n_clamped = 0;
+#define RG_PT(v) st_point<FAST, VARIANT, FULL, DEF, true>(cfg, &s_ea, (v), grid, n_clamped, stats, scan, 0, sm)
+        for (int k = 0; k < nt; ++k, ++g) {
+            const unsigned s = g % NST;
+            const int cnt = min(TILE, n - k * TILE);
+            mbar_wait(bar_full + 8u * s, (g / NST) & 1u);
+            const uint32_t base = ring + s * TILE_BYTES + (uint32_t)tid * 16u;
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (u * SC_THREADS + tid < cnt) v[u] = lds_f4(base + (uint32_t)u * (SC_THREADS * 16u));
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_empty + 8u * s);      // this warp has its points in registers
+            if (tid == 0 && k + NST < nt) {
+                const int cn = min(TILE, n - (k + NST) * TILE);
+                request(g + NST, src + (size_t)(k + NST) * TILE_BYTES, (uint32_t)cn * 16u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (u * SC_THREADS + tid < cnt) RG_PT(v[u]);
+        }
+#undef RG_PT
+        if (stats) {
+            unsigned long long *st = stats + (int64_t)scan * 6;
+            const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
+            if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
+            if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
+        }
+        // the next item's first tiles go out now, so that they land while this item is decoded
+        if (tid == 0) prologue(s_next[par ^ 1], g);
+        sc_finish_item<SPLIT>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
+        par ^= 1;
+        item = s_next[par];
     }
 }
 
@@ -956,13 +1208,38 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
     int rc;
     if (stats) DSC_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(dsc_scan_stats) * (size_t)n_scans, st));
-    // ---- main path: one persistent CTA per scan, private L2-resident key slots ----
-    const bool sc_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0 &&
-                       (ctx->k1_impl == 0 ? n_scans >= ctx->sm_count / 2 : ctx->k1_impl == 3);
+    // ---- main path: persistent CTAs, one scan (or one slice of a big scan) at a time ----
+    // Work items: a scan is cut into `parts` point ranges of about sc_item_points points when one CTA per
+    // scan would not fill the chip (few scans, or multi-million-point scans); see k1_scan<SPLIT>.
+    int64_t total_pts = 0, max_pts = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        const int64_t n = h_offsets[s + 1] - h_offsets[s];
+        total_pts += n;
+        if (n > max_pts) max_pts = n;
+    }
+    int64_t item_pts = ctx->sc_item_points;
+    {   // small batches: shrink the items until every SM gets a few of them (not below 16 Ki points)
+        const int64_t want = total_pts / ((int64_t)ctx->sm_count * 4);
+        if (want < item_pts) item_pts = want < 16384 ? 16384 : want;
+    }
+    int64_t split_items = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        const int64_t n = h_offsets[s + 1] - h_offsets[s];
+        split_items += n > item_pts ? (n + item_pts - 1) / item_pts : 1;
+    }
+    const bool sc_shape_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0;
+    const bool want_split = ctx->sc_split == 1 ||
+                            (ctx->sc_split < 0 && (n_scans < 2 * ctx->sm_count || max_pts > 3 * ctx->sc_item_points) &&
+                             split_items > n_scans);
+    const bool split = sc_shape_ok && want_split && (ctx->k1_impl == 0 || ctx->k1_impl == 3) &&
+                       split_items < 0x7fff0000LL;
+    const bool sc_ok = sc_shape_ok &&
+                       (split || (ctx->k1_impl == 0 ? n_scans >= ctx->sm_count / 2 : ctx->k1_impl == 3));
     if (sc_ok) {
         int ctas = ctx->sm_count;
-        if (ctas > n_scans) ctas = n_scans;
-        const size_t need = (size_t)ctx->sm_count * cells * 4;
+        const int64_t n_items = split ? split_items : (int64_t)n_scans;
+        if (ctas > n_items) ctas = (int)n_items;
+        const size_t need = split ? 0 : (size_t)ctx->sm_count * cells * 4;
         if (need > ctx->keys_bytes) {
             if (ctx->keys) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->keys); }
             ctx->keys = nullptr;
@@ -971,55 +1248,113 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             ctx->keys_bytes = need;
             DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
         }
-        if ((rc = dsc_reserve_sync(ctx, 256))) return rc;
-        // optional: pin the key slots in L2 with a persisting access-policy window on the launch stream
-        cudaStreamAttrValue win;
-        memset(&win, 0, sizeof win);
-        if (ctx->l2_persist && ctx->persist_max > 0) {
-            if (!ctx->persist_set) {
-                const size_t lim = need < ctx->persist_max ? need : ctx->persist_max;
-                DSC_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim));
-                ctx->persist_set = lim;
+        // sync block: [cursor (16 B)] [done[n_scans]] [item_base[n_scans+1] (ragged batches)]
+        SplitArgs spa = {nullptr, nullptr, 0, 0};
+        size_t sync_bytes = 16;
+        if (split) {
+            bool uniform = true;
+            const int64_t n0 = h_offsets[1] - h_offsets[0];
+            for (int s = 1; s < n_scans && uniform; ++s) uniform = (h_offsets[s + 1] - h_offsets[s]) == n0;
+            const size_t done_bytes = ((size_t)n_scans * 4 + 15) & ~(size_t)15;
+            const size_t tb_bytes = uniform ? 0 : sizeof(int64_t) * ((size_t)n_scans + 1);
+            if ((rc = dsc_reserve_sync(ctx, 16 + done_bytes + tb_bytes + 64))) return rc;
+            spa.done = (unsigned int *)((uint8_t *)ctx->sync_buf + 16);
+            spa.total_items = (int)split_items;
+            if (uniform) {
+                spa.parts_uniform = (int)(split_items / n_scans);
+            } else {
+                int64_t *d_tb = (int64_t *)((uint8_t *)ctx->sync_buf + 16 + done_bytes);
+                std::vector<int64_t> tb((size_t)n_scans + 1);
+                int64_t acc_t = 0;
+                for (int s = 0; s < n_scans; ++s) {
+                    const int64_t n = h_offsets[s + 1] - h_offsets[s];
+                    tb[s] = acc_t;
+                    acc_t += n > item_pts ? (n + item_pts - 1) / item_pts : 1;
+                }
+                tb[n_scans] = acc_t;
+                // pageable source: the copy is staged by the driver before the call returns
+                DSC_CUDA(ctx, cudaMemcpyAsync(d_tb, tb.data(), tb_bytes, cudaMemcpyHostToDevice, st));
+                spa.item_base = d_tb;
             }
-            win.accessPolicyWindow.base_ptr = ctx->keys;
-            win.accessPolicyWindow.num_bytes = need < ctx->window_max ? need : ctx->window_max;
-            const double ratio = (double)ctx->persist_set / (double)win.accessPolicyWindow.num_bytes;
-            win.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
-            win.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            win.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
+            sync_bytes = 16 + done_bytes;
+            // the output grids double as the key grids of their scans: start from "empty"
+            DSC_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)n_scans * cells * 4, st));
+        } else {
+            if ((rc = dsc_reserve_sync(ctx, 256))) return rc;
         }
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
-        DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, 16, st));
+        DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, sync_bytes, st));
         unsigned long long *stp = (unsigned long long *)stats;
+        const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
+        const bool full = p->full_height != 0;
+        const size_t row_bytes = (size_t)p->num_sector * 4;
+        // ---- TMA-ring loader (k1_ring): default grid + screened path only; everything else uses k1_scan ----
+        const int ring_cfg = (cfg.fast_ok && defgrid) ? ctx->sc_loader : 0;
+        if (ring_cfg > 0) {
+            // ring_cfg: 1 = 1 pt/thread x 4 stages (64 KB), 2 = 2 x 3 (96 KB), 3 = 1 x 6 (96 KB), 4 = 1 x 3 (48 KB)
+            const size_t ring_bytes = ring_cfg == 1 ? 65536 : ring_cfg == 4 ? 49152 : 98304;
+            int ns = (int)((ctx->smem_optin - ring_bytes - 1024) / row_bytes);
+            if (ctx->sc_smem_rows >= 0 && ctx->sc_smem_rows < ns) ns = ctx->sc_smem_rows;
+            if (ns > p->num_ring) ns = p->num_ring;
+            if (ns < 2) ns = 0;
+            const size_t rg_smem = (((size_t)ns * row_bytes + 127) & ~(size_t)127) + ring_bytes;
+#define RG_LAUNCH3(V, H, U, N, SP)                                                                              \
+    do {                                                                                                        \
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_ring<true, V, H, U, N, true, SP>,                                 \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rg_smem));         \
+        k1_ring<true, V, H, U, N, true, SP><<<ctas, SC_THREADS, rg_smem, st>>>(pts, d_offsets, n_scans,         \
+                                                                               ctx->keys, out, stp, cursor, ns, \
+                                                                               cfg, spa);                       \
+    } while (0)
+#define RG_LAUNCH2(V, H, U, N)                                                                                  \
+    do {                                                                                                        \
+        if (split) RG_LAUNCH3(V, H, U, N, true); else RG_LAUNCH3(V, H, U, N, false);                            \
+    } while (0)
+#define RG_LAUNCH(V, H)                                                                                         \
+    do {                                                                                                        \
+        if (ring_cfg == 1) RG_LAUNCH2(V, H, 1, 4);                                                              \
+        else if (ring_cfg == 2) RG_LAUNCH2(V, H, 2, 3);                                                         \
+        else if (ring_cfg == 3) RG_LAUNCH2(V, H, 1, 6);                                                         \
+        else RG_LAUNCH2(V, H, 1, 3);                                                                            \
+    } while (0)
+            if (p->variant == 0) { if (full) RG_LAUNCH(0, true); else RG_LAUNCH(0, false); }
+            else                 { if (full) RG_LAUNCH(1, true); else RG_LAUNCH(1, false); }
+#undef RG_LAUNCH
+#undef RG_LAUNCH2
+#undef RG_LAUNCH3
+            if ((rc = dsc_check_launch(ctx, "k1_ring"))) return rc;
+            if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
+            return DSC_OK;
+        }
         // resident ring rows.  Shared memory and L1 share 256 KB per SM and the 128-bit streaming loads
         // land in L1: with the grid rows taking the full 227 KB the kernel loses 20 % (measured sweep in
         // profiles/r1_notes.md), so stay inside the 164 KB carve-out step: 56 of 160 rows for S = 720.
         const size_t sc_budget = (size_t)164 * 1024 - 1024 - 256;
-        int ns = (int)((sc_budget < ctx->smem_optin ? sc_budget : ctx->smem_optin - 1024) / ((size_t)p->num_sector * 4));
+        int ns = (int)((sc_budget < ctx->smem_optin ? sc_budget : ctx->smem_optin - 1024) / row_bytes);
         if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                     // A/B override
-        if ((size_t)ns * p->num_sector * 4 + 1024 > ctx->smem_optin) ns = (int)((ctx->smem_optin - 1024) / ((size_t)p->num_sector * 4));
+        if ((size_t)ns * row_bytes + 1024 > ctx->smem_optin) ns = (int)((ctx->smem_optin - 1024) / row_bytes);
         if (ns > p->num_ring) ns = p->num_ring;
         if (ns < 2) ns = 0;
-        const size_t sc_smem = (size_t)ns * p->num_sector * 4;
-#define SC_LAUNCH3(F, V, H, U, HN, D)                                                                           \
+        const size_t sc_smem = (size_t)ns * row_bytes;
+#define SC_LAUNCH4(F, V, H, U, D, SP)                                                                           \
     do {                                                                                                        \
-        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, HN, D>,                                          \
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, 1, D, SP>,                                       \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
-        k1_scan<F, V, H, U, HN, D><<<ctas, SC_THREADS, sc_smem, st>>>(pts, d_offsets, n_scans, ctx->keys, out,  \
-                                                                      stp, cursor, ns, cfg);                    \
+        k1_scan<F, V, H, U, 1, D, SP><<<ctas, SC_THREADS, sc_smem, st>>>(pts, d_offsets, n_scans, ctx->keys,    \
+                                                                         out, stp, cursor, ns, cfg, spa);       \
     } while (0)
-#define SC_LAUNCH2(F, V, H, U, HN)                                                                              \
+#define SC_LAUNCH3(F, V, H, U, D)                                                                               \
     do {                                                                                                        \
-        if (F && defgrid) SC_LAUNCH3(F, V, H, U, HN, true); else SC_LAUNCH3(F, V, H, U, HN, false);             \
+        if (split) SC_LAUNCH4(F, V, H, U, D, true); else SC_LAUNCH4(F, V, H, U, D, false);                      \
+    } while (0)
+#define SC_LAUNCH2(F, V, H, U)                                                                                  \
+    do {                                                                                                        \
+        if (F && defgrid) SC_LAUNCH3(F, V, H, U, true); else SC_LAUNCH3(F, V, H, U, false);                     \
     } while (0)
 #define SC_LAUNCH(F, V, H)                                                                                      \
     do {                                                                                                        \
-        if (ctx->l2_hints == 0) { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 0); else SC_LAUNCH2(F, V, H, 2, 0); } \
-        else { if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3, 1); else SC_LAUNCH2(F, V, H, 2, 1); }             \
+        if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3); else SC_LAUNCH2(F, V, H, 2);                              \
     } while (0)
-        const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
-        const bool full = p->full_height != 0;
         if (cfg.fast_ok) {
             if (p->variant == 0) { if (full) SC_LAUNCH(true, 0, true); else SC_LAUNCH(true, 0, false); }
             else                 { if (full) SC_LAUNCH(true, 1, true); else SC_LAUNCH(true, 1, false); }
@@ -1030,11 +1365,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
 #undef SC_LAUNCH
 #undef SC_LAUNCH2
 #undef SC_LAUNCH3
+#undef SC_LAUNCH4
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
-        if (win.accessPolicyWindow.num_bytes) {      // leave the caller's stream as we found it
-            win.accessPolicyWindow.num_bytes = 0;
-            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
-        }
         if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
         return DSC_OK;
     }

@@ -6,6 +6,7 @@ stream provider here -- every kernel that runs is in libdsc.so).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -102,15 +103,27 @@ class Engine:
         rc = self._lib.dsc_create(int(device), C.byref(h))
         if rc != _ffi.DSC_OK:
             raise _ffi.DscError(rc, "dsc_create failed (no CUDA device? the engine has no CPU fallback)")
-        self._h = h
+        self._handle = h
+        self._pid = os.getpid()
         self.device = int(device)
         self._tables_key = None
 
+    @property
+    def _h(self):
+        # a CUDA context does not survive fork(): DataLoader(num_workers>0) children must not use the
+        # parent's engine (kitti_dataloader.py builds its loader with fork workers)
+        if self._pid != os.getpid():
+            raise RuntimeError("dsc engine used from a forked child process: CUDA cannot be used after fork(); "
+                               "run the DataLoader with num_workers=0 or multiprocessing_context='spawn'")
+        if self._handle is None:
+            raise RuntimeError("dsc engine is closed")
+        return self._handle
+
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
-        if getattr(self, "_h", None):
-            self._lib.dsc_destroy(self._h)
-            self._h = None
+        if getattr(self, "_handle", None) is not None and self._pid == os.getpid():
+            self._lib.dsc_destroy(self._handle)
+        self._handle = None
 
     def __del__(self):
         try:
@@ -313,6 +326,6 @@ def default_engine(device: int = 0) -> Engine:
     """Process-wide engine per device, created on first use."""
     with _default_lock:
         e = _default.get(device)
-        if e is None:
+        if e is None or e._handle is None or e._pid != os.getpid():
             e = _default[device] = Engine(device)
         return e

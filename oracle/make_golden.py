@@ -13,6 +13,7 @@ Fixtures
                        np.arctan2 values this host produced, because float32 arctan2 is host dependent:
                        SVML on AVX-512 hosts, libm elsewhere), rasteriser, reconstructor, to_tensor01
   tinycnn_logits.npz   TinyCNN(tinycnn_best.pth) fp32 CPU logits on to_tensor01(sc_000840)
+  tinycnn_best.pth     the reference's TinyCNN state_dict (data, 583 KB), used by the config-4 tests and bench
 """
 from __future__ import annotations
 
@@ -191,6 +192,8 @@ def main():
         x = tiny.to_tensor01(np.load(os.path.join(td, "sc_000840.npy"))).unsqueeze(0)
         logits = model(x)[0, 0].numpy()
     np.savez_compressed(os.path.join(OUT, "tinycnn_logits.npz"), logits=logits)
+    # the weights are reference *data* (like the scans): config 4 needs them on the GPU box
+    shutil.copyfile(os.path.join(ref.REF_ROOT, "distro_model", "tinycnn_best.pth"), os.path.join(OUT, "tinycnn_best.pth"))
     info = {"numpy": np.__version__, "torch": torch.__version__,
             "note": "float32 arctan2 flavour of this host is recorded per case in ref_live.npz (*__atan2)"}
     with open(os.path.join(OUT, "README.json"), "w") as f:

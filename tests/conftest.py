@@ -62,12 +62,15 @@ def orc():
     return oracle
 
 
-@pytest.fixture(scope="session", params=["auto", "l2keys", "halfgrid", "scan", "tile"])
+@pytest.fixture(scope="session", params=["auto", "l2keys", "halfgrid", "scan", "scan_nosplit", "tile"])
 def engine(request):
-    """One engine per K1 implementation: the default streaming kernel and the two A/B variants."""
+    """One engine per K1 implementation: the default (persistent scan kernel; small batches and big scans are
+    split into work items) and the A/B variants."""
     from distropointclouds_b200.engine import Engine
     e = Engine(0)
-    e.set_option("k1_impl", {"auto": 0, "l2keys": 1, "halfgrid": 2, "scan": 3, "tile": 4}[request.param])
+    e.set_option("k1_impl", {"auto": 0, "l2keys": 1, "halfgrid": 2, "scan": 3, "scan_nosplit": 3, "tile": 4}[request.param])
+    if request.param == "scan_nosplit":
+        e.set_option("sc_split", 0)          # one CTA per scan even for tiny batches
     yield e
     e.close()
 
