@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--workload", default="kitti120k", choices=sorted(WORKLOADS))
     ap.add_argument("--scans", type=int, default=0, help="scans per GPU per step (0: the workload's)")
     ap.add_argument("--points", type=int, default=0, help="points per scan (0: the workload's)")
-    ap.add_argument("--cnn-precision", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--cnn-precision", default="tf32", choices=["fp32", "tf32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     # A/B knobs of the engine (see dsc_api.cu); None = engine default

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsc.so")
+LIB_PATH = os.environ.get("DSC_LIB") or os.path.join(_HERE, "libdsc.so")     # DSC_LIB: A/B builds only
 
 DSC_OK, DSC_ERR_INVALID, DSC_ERR_CUDA, DSC_ERR_NOMEM, DSC_ERR_CAPACITY = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -26,6 +26,7 @@ extern "C" int dsc_create(int device, dsc_ctx **out)
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if (const char *e = getenv("DSC_K1_IMPL")) ctx->k1_impl = atoi(e);   // debugging / A-B benchmarking only
     if (const char *e = getenv("DSC_SC_LOADER")) ctx->sc_loader = atoi(e);
+    if (const char *e = getenv("DSC_SC_CFG")) ctx->sc_cfg = atoi(e);
     bool ok = cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess &&
@@ -77,10 +78,10 @@ extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "k1_impl") && value >= 0 && value <= 4) { ctx->k1_impl = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_smem_rows") && value >= -1 && value <= 65536) { ctx->sc_smem_rows = (int)value; return DSC_OK; }
     if (!strcmp(name, "no_defgrid") && value >= 0 && value <= 1) { ctx->no_defgrid = (int)value; return DSC_OK; }
-    if (!strcmp(name, "sc_loader") && value >= 0 && value <= 4) { ctx->sc_loader = (int)value; return DSC_OK; }
+    if (!strcmp(name, "sc_loader") && value >= 0 && value <= 1) { ctx->sc_loader = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_split") && value >= -1 && value <= 1) { ctx->sc_split = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_item_points") && value >= 1024 && value <= (1 << 30)) { ctx->sc_item_points = (int)value; return DSC_OK; }
-    if (!strcmp(name, "sc_cfg") && value >= 0 && value <= 1) { ctx->sc_cfg = (int)value; return DSC_OK; }
+    if (!strcmp(name, "sc_cfg") && value >= 0 && value <= 2) { ctx->sc_cfg = (int)value; return DSC_OK; }
     if (!strcmp(name, "st_cfg") && value >= 0 && value <= 1) { ctx->st_cfg = (int)value; return DSC_OK; }
     if (!strcmp(name, "st_slots") && value >= 1 && value <= 4096) { ctx->st_slots = (int)value; return DSC_OK; }
     if (!strcmp(name, "pf_dist") && value >= 0 && value <= 64) { ctx->pf_dist = (int)value; return DSC_OK; }

@@ -155,12 +155,6 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t l2_policy_evict_last()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ float4 ld_stream_f4_hint(const void *p, uint64_t pol)
 {
     float4 v;
@@ -436,8 +430,8 @@ __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea,
                                          unsigned long long *__restrict__ stats, int scan, uint64_t key_policy = 0,
                                          const SmemRows sm = SmemRows{0u, 0, 0x7fffffff})
 {
-    int ring, sector;
-    bool beyond, ok = false;
+    int ring = 0, sector = 0;
+    bool beyond = false, ok = false;
     if constexpr (FAST) {
         ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
         if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
@@ -669,6 +663,9 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
 // 128-bit streaming stores), re-zeroes it and moves on.  There is no synchronisation between CTAs at all;
 // HBM sees each point once and each output cell once.
 constexpr int SC_THREADS = 1024;
+#ifndef SC_DU
+#define SC_DU 4                       // 128-bit L2 loads in flight per thread in the decode
+#endif
 
 // SPLIT = true: a scan is cut into `parts` contiguous point ranges (work items) that different CTAs
 // process concurrently -- for multi-million-point scans and for batches with fewer scans than SMs, where
@@ -682,6 +679,118 @@ struct SplitArgs {
     int total_items;
     int parts_uniform;           // > 0: every scan has this many items
 };
+
+// ---- deferred exact path ------------------------------------------------------------------------------------
+// A point that fails the screen needs the ~200-instruction fdlibm chain.  Only ~0.3 % of the points do, but
+// taken inline that is a divergent branch which some lane of a warp takes every ~7th point, so the warp as a
+// whole spends a quarter of its issue slots there with one or two lanes active.  Instead every warp parks such
+// points in a small shared-memory queue (x[64], y[64], z[64]) and runs the exact chain only when 32 are
+// waiting -- all lanes busy -- or when the work item ends.
+constexpr int SCQ_CAP = 64;                                   // entries per warp
+constexpr int SCQ_WARP_BYTES = SCQ_CAP * 12;                  // 768 B per warp
+
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// fold one binned point into the key grid: resident rows -> LDS pre-check + ATOMS.MAX, other rows -> RED.MAX (L2)
+template <bool FULL>
+__device__ __forceinline__ void sc_update(const float zv, const int cell, uint32_t *__restrict__ grid, const SmemRows sm)
+{
+    const uint32_t u = __float_as_uint(zv);
+    const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
+    if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
+    if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
+    if (cell < sm.lim || cell >= sm.last) {
+        const int local = cell < sm.lim ? cell : cell - sm.last + sm.lim;       // clamp ring -> row ns-1
+        const uint32_t addr = sm.base + (uint32_t)local * 4u;
+        if (key > lds_u32(addr)) reds_max_u32(addr, key);   // most points are not a new maximum
+        return;
+    }
+    red_max_global(grid + cell, key);
+}
+
+// exact chain for one queued point (entry address of this lane); returns 1 if the point was clamped into the last ring
+template <int VARIANT, bool FULL>
+__device__ __noinline__ unsigned sc_exact_queued(uint32_t qaddr, const ExactArgs *__restrict__ ea,
+                                                 uint32_t *__restrict__ grid, uint32_t sm_base, int sm_lim, int sm_last,
+                                                 unsigned long long *__restrict__ st)
+{
+    const float x = lds_f32(qaddr), y = lds_f32(qaddr + SCQ_CAP * 4), z = lds_f32(qaddr + SCQ_CAP * 8);
+    const uint2 b = hg_bin_exact<VARIANT, FULL>(x, y, z, ea);
+    const int status = (int)(b.x >> 27), cell = (int)(b.x & 0x7ffffffu);
+    if (st) {                                    // rare events: straight to the per-scan counters
+        atomicAdd(st + 5, 1ull);
+        if (status == dsc::PT_NONFINITE) atomicAdd(st + 1, 1ull);
+        if (status == dsc::PT_SECTOR_OVERFLOW) atomicAdd(st + 2, 1ull);
+        if (status == dsc::PT_OUT_OF_RANGE) atomicAdd(st + 4, 1ull);
+    }
+    if (status > dsc::PT_CLAMPED) return 0u;
+    sc_update<FULL>(__uint_as_float(b.y), cell, grid, SmemRows{sm_base, sm_lim, sm_last});
+    return status == dsc::PT_CLAMPED ? 1u : 0u;
+}
+
+// One point per lane, called warp-uniformly (`active` masks lanes past the end of the item).
+template <int VARIANT, bool FULL, bool DEF>
+__device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v, const bool active,
+                                         uint32_t *__restrict__ grid, unsigned &n_clamped,
+                                         unsigned long long *__restrict__ st, const SmemRows sm,
+                                         const uint32_t queue, unsigned &qcount)
+{
+    int ring, sector;
+    bool beyond;
+    bool ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
+    if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
+    if (ok && active) {
+        if (VARIANT == 1 && beyond) {
+            if (st) atomicAdd(st + 4, 1ull);
+        } else {
+            if (VARIANT == 0) n_clamped += beyond;
+            const int S = DEF ? dsc::defgrid::S : cfg.S;
+            sc_update<FULL>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, grid, sm);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, active && !ok);
+    if (m) {                                     // warp-uniform, rare
+        const unsigned lane = threadIdx.x & 31u;
+        if (active && !ok) {
+            const uint32_t a = queue + (qcount + __popc(m & ((1u << lane) - 1u))) * 4u;
+            sts_f32(a, v.x);
+            sts_f32(a + SCQ_CAP * 4, v.y);
+            sts_f32(a + SCQ_CAP * 8, v.z);
+        }
+        qcount += __popc(m);
+        if (qcount >= 32u) {
+            qcount -= 32u;
+            __syncwarp();
+            n_clamped += sc_exact_queued<VARIANT, FULL>(queue + (qcount + lane) * 4u, ea, grid, sm.base, sm.lim, sm.last, st);
+            __syncwarp();
+        }
+    }
+}
+
+// end of item: the queue's remaining entries (fewer than 32)
+template <int VARIANT, bool FULL>
+__device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *__restrict__ grid, unsigned &n_clamped,
+                                         unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t queue,
+                                         unsigned &qcount)
+{
+    if (qcount) {
+        const unsigned lane = threadIdx.x & 31u;
+        __syncwarp();
+        if (lane < qcount)
+            n_clamped += sc_exact_queued<VARIANT, FULL>(queue + lane * 4u, ea, grid, sm.base, sm.lim, sm.last, st);
+        __syncwarp();
+        qcount = 0;
+    }
+}
 
 // work item -> (scan, first point, point count, parts of the scan, key grid)
 template <bool SPLIT>
@@ -710,10 +819,11 @@ __device__ __forceinline__ void sc_item(int item, const int64_t *__restrict__ of
 // L2 slot to floats (coalesced 128-bit streaming stores) and re-zero both.  Split: fold the resident rows
 // into the scan's key grid (== its output grid), count the item as retired, and if it was the scan's last
 // item decode the grid in place.  Ends with a CTA barrier in both cases.
-template <bool SPLIT>
+template <bool SPLIT, int NT, int DU = 4>
 __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid,
                                                float *__restrict__ out_scan, int ns, int R, int S, int scan, int parts,
-                                               unsigned int *__restrict__ done, int *s_last)
+                                               unsigned int *__restrict__ done, int *s_last,
+                                               unsigned int *__restrict__ reset = nullptr)
 {
     const int tid = threadIdx.x;
     const int rowvec = S >> 2;
@@ -722,7 +832,7 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
     const int lim = (ns - 1) * rowvec, shift = (R - ns) * rowvec;    // resident row ns-1 holds ring R-1
     if constexpr (SPLIT) {
         __syncthreads();                         // every shared-memory atomic of the item has landed
-        for (int i = tid; i < nres; i += SC_THREADS) {
+        for (int i = tid; i < nres; i += NT) {
             const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
             if ((q.x | q.y | q.z | q.w) == 0u) continue;
             reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
@@ -735,6 +845,7 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
         __threadfence();                         // release: this CTA's REDs are performed ...
         __syncthreads();
         if (tid == 0) {
+            if (reset) *reset = 0u;              // every warp has left the item's streaming loop
             const unsigned prev = atomicAdd(done + scan, 1u);          // ... before the item counts as retired
             *s_last = prev + 1u == (unsigned)parts;
             if (prev + 1u == (unsigned)parts) __threadfence();         // acquire: the other CTAs' REDs are visible
@@ -743,17 +854,16 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
         if (*s_last) {
             uint4 *kq = reinterpret_cast<uint4 *>(grid);
             const int nvec = cells >> 2;
-            constexpr int DU = 4;
-            for (int i0 = tid; i0 < nvec; i0 += SC_THREADS * DU) {
+            for (int i0 = tid; i0 < nvec; i0 += NT * DU) {
                 uint4 q[DU];
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * SC_THREADS;
+                    const int i = i0 + d * NT;
                     if (i < nvec) q[d] = __ldcg(kq + i);
                 }
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * SC_THREADS;
+                    const int i = i0 + d * NT;
                     if (i < nvec) {
                         float4 f;
                         f.x = dsc::key_to_float(q[d].x);
@@ -769,8 +879,9 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
     } else {
         __threadfence();                         // our REDs are performed ...
         __syncthreads();                         // ... before any thread of the CTA reads the keys back
+        if (tid == 0 && reset) *reset = 0u;      // every warp has left the item's streaming loop
         float4 *oq = reinterpret_cast<float4 *>(out_scan);
-        for (int i = tid; i < nres; i += SC_THREADS) {       // resident rows: rings 0 .. ns-2 and the clamp ring
+        for (int i = tid; i < nres; i += NT) {       // resident rows: rings 0 .. ns-2 and the clamp ring
             const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
             reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
             float4 f;
@@ -784,17 +895,16 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
             const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
             uint4 *kz = reinterpret_cast<uint4 *>(grid);
             const int lo = (ns > 0 ? ns - 1 : 0) * rowvec, hi = (ns > 0 ? R - 1 : R) * rowvec;
-            constexpr int DU = 4;
-            for (int i0 = lo + tid; i0 < hi; i0 += SC_THREADS * DU) {
+            for (int i0 = lo + tid; i0 < hi; i0 += NT * DU) {
                 uint4 q[DU];
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * SC_THREADS;
+                    const int i = i0 + d * NT;
                     if (i < hi) q[d] = __ldcg(kq + i);
                 }
 #pragma unroll
                 for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * SC_THREADS;
+                    const int i = i0 + d * NT;
                     if (i < hi) {
                         float4 f;
                         f.x = dsc::key_to_float(q[d].x);
@@ -812,14 +922,18 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
     }
 }
 
-template <bool FAST, int VARIANT, bool FULL, int U, int HINTS, bool DEF, bool SPLIT>
-__global__ void __launch_bounds__(SC_THREADS, 1)
+template <bool FAST, int VARIANT, bool FULL, int U, int NT, bool DEF, bool SPLIT>
+__global__ void __launch_bounds__(NT, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
         unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg, const SplitArgs sp)
 {
-    constexpr int STEP = SC_THREADS * U;
-    extern __shared__ __align__(16) uint32_t srows[];          // ns ring rows of keys
+    // NB: this kernel lives on the edge of its register budget (64 regs at 1024 threads, 80 at 768); measured
+    // variants that carried more state across the streaming loop (next-item prefetch before the decode,
+    // per-warp chunk counters, 8 decode loads in flight) spilled inside the loop and lost 15-40 %
+    // (profiles/r1_notes.md).
+    constexpr int STEP = NT * U;
+    extern __shared__ __align__(16) uint32_t srows[];          // [ns ring rows of keys][per-warp exact-path queues]
     __shared__ int s_next[2];
     __shared__ int s_last;
     __shared__ ExactArgs s_ea;
@@ -828,12 +942,15 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int cells = R * S;
     const int rowvec = S >> 2;                   // host guarantees S % 4 == 0
     uint32_t *grid = SPLIT ? nullptr : keys + (size_t)blockIdx.x * cells;
-    const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
+    const uint64_t pol_stream = l2_policy_evict_first();
     SmemRows sm;
     sm.base = (uint32_t)__cvta_generic_to_shared(srows);
     sm.lim = ns > 0 ? (ns - 1) * S : 0;
     sm.last = ns > 0 ? (R - 1) * S : 0x7fffffff;
-    for (int i = tid; i < ns * rowvec; i += SC_THREADS) reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+    // per-warp queue of points waiting for the exact chain, behind the resident rows
+    const uint32_t queue = sm.base + (uint32_t)ns * (uint32_t)S * 4u + (uint32_t)(tid >> 5) * SCQ_WARP_BYTES;
+    unsigned qcount = 0;
+    for (int i = tid; i < ns * rowvec; i += NT) reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         fill_exact_args(&s_ea, cfg);
         s_next[0] = (int)atomicAdd(cursor, 1u);
@@ -851,44 +968,54 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
         if constexpr (SPLIT) grid = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
         const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         unsigned n_clamped = 0;
+        unsigned long long *st = stats ? stats + (int64_t)scan * 6 : nullptr;
         const int nfull = n / STEP;
         const float4 *p = s4 + tid;
         float4 a[U], b[U];
-#define SC_LD(ptr) (HINTS ? ld_stream_f4_hint((ptr), pol_stream) : ld_stream_f4((ptr)))
-#define SC_PT(v) st_point<FAST, VARIANT, FULL, DEF, true>(cfg, &s_ea, (v), grid, n_clamped, stats, scan, 0, sm)
+#define SC_LD(ptr) ld_stream_f4_hint((ptr), pol_stream)
+#define SC_PT(v, act)                                                                                           \
+    do {                                                                                                        \
+        if constexpr (FAST) sc_point<VARIANT, FULL, DEF>(cfg, &s_ea, (v), (act), grid, n_clamped, st, sm, queue, qcount); \
+        else if (act) st_point<false, VARIANT, FULL, DEF, true>(cfg, &s_ea, (v), grid, n_clamped, stats, scan, 0, sm);   \
+    } while (0)
         if (nfull > 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * SC_THREADS);
+            for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
         }
         int step = 0;
         while (step + 1 < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * SC_THREADS);
+            for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * NT);
 #pragma unroll
-            for (int u = 0; u < U; ++u) SC_PT(a[u]);
+            for (int u = 0; u < U; ++u) SC_PT(a[u], true);
             p += 2 * STEP;
             step += 2;
             if (step < nfull) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * SC_THREADS);
+                for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) SC_PT(b[u]);
+            for (int u = 0; u < U; ++u) SC_PT(b[u], true);
         }
         if (step < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) SC_PT(a[u]);
+            for (int u = 0; u < U; ++u) SC_PT(a[u], true);
         }
-        for (int i = nfull * STEP + tid; i < n; i += SC_THREADS) SC_PT(SC_LD(s4 + i));   // ragged tail
+        for (int i0 = nfull * STEP; i0 < n; i0 += NT) {       // ragged tail, warp-uniform trip count
+            const bool act = i0 + tid < n;
+            float4 v = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+            if (act) v = SC_LD(s4 + i0 + tid);
+            SC_PT(v, act);
+        }
+        if constexpr (FAST) sc_drain<VARIANT, FULL>(&s_ea, grid, n_clamped, st, sm, queue, qcount);
 #undef SC_LD
 #undef SC_PT
         if (stats) {
-            unsigned long long *st = stats + (int64_t)scan * 6;
             const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
             if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
             if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
         }
-        sc_finish_item<SPLIT>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
+        sc_finish_item<SPLIT, NT, SC_DU>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
         par ^= 1;
         item = s_next[par];                      // published by the barriers of sc_finish_item
     }
@@ -946,7 +1073,7 @@ k1_ring(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 {
     constexpr int TILE = SC_THREADS * U;                       // points per tile
     constexpr uint32_t TILE_BYTES = TILE * 16u;
-    extern __shared__ __align__(128) uint32_t srows[];         // [ns ring rows of keys][NST tiles]
+    extern __shared__ __align__(16) uint32_t srows[];          // [ns ring rows of keys][NST tiles]
     __shared__ __align__(8) unsigned long long s_bar[2 * NST];  // full[NST], empty[NST]
     __shared__ int s_next[2];
     __shared__ int s_last;
@@ -1040,7 +1167,7 @@ k1_ring(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
         }
         // the next item's first tiles go out now, so that they land while this item is decoded
         if (tid == 0) prologue(s_next[par ^ 1], g);
-        sc_finish_item<SPLIT>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
+        sc_finish_item<SPLIT, SC_THREADS>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
         par ^= 1;
         item = s_next[par];
     }
@@ -1291,8 +1418,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         // ---- TMA-ring loader (k1_ring): default grid + screened path only; everything else uses k1_scan ----
         const int ring_cfg = (cfg.fast_ok && defgrid) ? ctx->sc_loader : 0;
         if (ring_cfg > 0) {
-            // ring_cfg: 1 = 1 pt/thread x 4 stages (64 KB), 2 = 2 x 3 (96 KB), 3 = 1 x 6 (96 KB), 4 = 1 x 3 (48 KB)
-            const size_t ring_bytes = ring_cfg == 1 ? 65536 : ring_cfg == 4 ? 49152 : 98304;
+            // 2 points per thread x 3 stages (96 KB); 1 x 4, 1 x 6 and 1 x 3 were measured and are slower (r1_notes.md)
+            const size_t ring_bytes = 98304;
             int ns = (int)((ctx->smem_optin - ring_bytes - 1024) / row_bytes);
             if (ctx->sc_smem_rows >= 0 && ctx->sc_smem_rows < ns) ns = ctx->sc_smem_rows;
             if (ns > p->num_ring) ns = p->num_ring;
@@ -1312,10 +1439,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     } while (0)
 #define RG_LAUNCH(V, H)                                                                                         \
     do {                                                                                                        \
-        if (ring_cfg == 1) RG_LAUNCH2(V, H, 1, 4);                                                              \
-        else if (ring_cfg == 2) RG_LAUNCH2(V, H, 2, 3);                                                         \
-        else if (ring_cfg == 3) RG_LAUNCH2(V, H, 1, 6);                                                         \
-        else RG_LAUNCH2(V, H, 1, 3);                                                                            \
+        RG_LAUNCH2(V, H, 2, 3);                                                                            \
     } while (0)
             if (p->variant == 0) { if (full) RG_LAUNCH(0, true); else RG_LAUNCH(0, false); }
             else                 { if (full) RG_LAUNCH(1, true); else RG_LAUNCH(1, false); }
@@ -1326,44 +1450,54 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
             return DSC_OK;
         }
-        // resident ring rows.  Shared memory and L1 share 256 KB per SM and the 128-bit streaming loads
-        // land in L1: with the grid rows taking the full 227 KB the kernel loses 20 % (measured sweep in
-        // profiles/r1_notes.md), so stay inside the 164 KB carve-out step: 56 of 160 rows for S = 720.
-        const size_t sc_budget = (size_t)164 * 1024 - 1024 - 256;
-        int ns = (int)((sc_budget < ctx->smem_optin ? sc_budget : ctx->smem_optin - 1024) / row_bytes);
+        // launch shape (threads x 128-bit loads per thread per register set); shapes other than 0 exist for the
+        // screened default-grid kernels only.  Fewer threads = more registers per thread (no spills), fewer warps.
+        int shape = (cfg.fast_ok && defgrid) ? ctx->sc_cfg : 2;                 // the generic kernels are 1024 x 2
+        if (shape != 1 && shape != 2) shape = 0;
+        const int nthreads = shape == 0 ? 768 : 1024;
+        const size_t q_bytes = cfg.fast_ok ? (size_t)SCQ_WARP_BYTES * (nthreads / 32) : 0;   // per-warp exact-path queues
+        // Resident rows.  Shared memory and L1 share 256 KB per SM and the 128-bit streaming loads stage through
+        // L1: beyond the 196 KB carve-out step (164 KB for the 1024-thread shapes) the loader starves
+        // (profiles/r1_notes.md: 60 rows 1.99 ms, 64 rows 2.14 ms).  Split scans have no private L2 slot --
+        // every non-resident point is a RED.MAX on a grid that 16 CTAs share -- and want every row they can get
+        // (dense2m: 62 rows 0.62 ms, 72 rows 0.53 ms).
+        const size_t sc_budget = split ? ctx->smem_optin
+                                       : (size_t)(nthreads < 1024 ? 196 : 164) * 1024 - 1024 - 256 - q_bytes;
+        const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
+        int ns = (int)((sc_budget < sc_max ? sc_budget : sc_max) / row_bytes);
         if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                     // A/B override
-        if ((size_t)ns * row_bytes + 1024 > ctx->smem_optin) ns = (int)((ctx->smem_optin - 1024) / row_bytes);
+        if ((size_t)ns * row_bytes > sc_max) ns = (int)(sc_max / row_bytes);
         if (ns > p->num_ring) ns = p->num_ring;
         if (ns < 2) ns = 0;
-        const size_t sc_smem = (size_t)ns * row_bytes;
-#define SC_LAUNCH4(F, V, H, U, D, SP)                                                                           \
+        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
+#define SC_LAUNCH4(F, V, H, U, NT, D, SP)                                                                       \
     do {                                                                                                        \
-        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, 1, D, SP>,                                       \
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP>,                                      \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
-        k1_scan<F, V, H, U, 1, D, SP><<<ctas, SC_THREADS, sc_smem, st>>>(pts, d_offsets, n_scans, ctx->keys,    \
-                                                                         out, stp, cursor, ns, cfg, spa);       \
+        k1_scan<F, V, H, U, NT, D, SP><<<ctas, NT, sc_smem, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, \
+                                                                  cursor, ns, cfg, spa);                        \
     } while (0)
-#define SC_LAUNCH3(F, V, H, U, D)                                                                               \
+#define SC_LAUNCH3(F, V, H, U, NT, D)                                                                           \
     do {                                                                                                        \
-        if (split) SC_LAUNCH4(F, V, H, U, D, true); else SC_LAUNCH4(F, V, H, U, D, false);                      \
+        if (split) SC_LAUNCH4(F, V, H, U, NT, D, true); else SC_LAUNCH4(F, V, H, U, NT, D, false);              \
     } while (0)
-#define SC_LAUNCH2(F, V, H, U)                                                                                  \
+#define SC_LAUNCH_DEF(V, H)                                                                                     \
     do {                                                                                                        \
-        if (F && defgrid) SC_LAUNCH3(F, V, H, U, true); else SC_LAUNCH3(F, V, H, U, false);                     \
+        if (shape == 1) SC_LAUNCH3(true, V, H, 3, 1024, true);                                                  \
+        else if (shape == 2) SC_LAUNCH3(true, V, H, 2, 1024, true);                                             \
+        else SC_LAUNCH3(true, V, H, 3, 768, true);                                                             \
     } while (0)
-#define SC_LAUNCH(F, V, H)                                                                                      \
-    do {                                                                                                        \
-        if (ctx->sc_cfg == 1) SC_LAUNCH2(F, V, H, 3); else SC_LAUNCH2(F, V, H, 2);                              \
-    } while (0)
-        if (cfg.fast_ok) {
-            if (p->variant == 0) { if (full) SC_LAUNCH(true, 0, true); else SC_LAUNCH(true, 0, false); }
-            else                 { if (full) SC_LAUNCH(true, 1, true); else SC_LAUNCH(true, 1, false); }
+        if (cfg.fast_ok && defgrid) {
+            if (p->variant == 0) { if (full) SC_LAUNCH_DEF(0, true); else SC_LAUNCH_DEF(0, false); }
+            else                 { if (full) SC_LAUNCH_DEF(1, true); else SC_LAUNCH_DEF(1, false); }
+        } else if (cfg.fast_ok) {
+            if (p->variant == 0) { if (full) SC_LAUNCH3(true, 0, true, 2, 1024, false); else SC_LAUNCH3(true, 0, false, 2, 1024, false); }
+            else                 { if (full) SC_LAUNCH3(true, 1, true, 2, 1024, false); else SC_LAUNCH3(true, 1, false, 2, 1024, false); }
         } else {
-            if (p->variant == 0) { if (full) SC_LAUNCH(false, 0, true); else SC_LAUNCH(false, 0, false); }
-            else                 { if (full) SC_LAUNCH(false, 1, true); else SC_LAUNCH(false, 1, false); }
+            if (p->variant == 0) { if (full) SC_LAUNCH3(false, 0, true, 2, 1024, false); else SC_LAUNCH3(false, 0, false, 2, 1024, false); }
+            else                 { if (full) SC_LAUNCH3(false, 1, true, 2, 1024, false); else SC_LAUNCH3(false, 1, false, 2, 1024, false); }
         }
-#undef SC_LAUNCH
-#undef SC_LAUNCH2
+#undef SC_LAUNCH_DEF
 #undef SC_LAUNCH3
 #undef SC_LAUNCH4
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;

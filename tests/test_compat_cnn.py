@@ -182,7 +182,7 @@ def test_patched_reference_shaped_classes_reproduce_golden(golden_scans, golden_
 def test_cnn_pipeline_logits_match_reference(golden_scans, golden_grids):
     """Config 4: packed points on the device -> K1 -> K4 -> TinyCNN.  Grids bit-exact; fp32 logits within
     2e-4 absolute of the reference's CPU fp32 logits (cuDNN vs oneDNN summation order; logits span -4.4..-2.8);
-    bf16 autocast within 5e-2."""
+    the opt-in fast modes (BN folded; tf32 / fp16 within 2e-2, bf16 within 1e-1)."""
     import torch
     from distropointclouds_b200.cnn import ScanContextCnnPipeline
     from distropointclouds_b200.engine import ScanContextParams
@@ -199,7 +199,7 @@ def test_cnn_pipeline_logits_match_reference(golden_scans, golden_grids):
     assert mask.dtype == torch.uint8 and int(mask[0].sum()) == int((1 / (1 + np.exp(-ref)) > 0.5).sum())
     g2, probs, m2 = pipe.infer_scans([s[:, :3] for s in scans])
     assert np.array_equal(g2[0], golden_grids["000840"]) and probs.shape == (2, 160, 720)
-    for prec, tol in (("tf32", 2e-2), ("bf16", 5e-2)):
+    for prec, tol in (("tf32", 2e-2), ("fp16", 2e-2), ("bf16", 1e-1)):
         fast = ScanContextCnnPipeline(w, 0, prec)
         _, lg, _ = fast.infer_device(pts, offs, ScanContextParams())
         np.testing.assert_allclose(lg[0].cpu().numpy(), ref, rtol=0, atol=tol)
