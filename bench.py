@@ -2,7 +2,7 @@
 """bench.py -- scan-context build throughput (BASELINE.json metric) on N B200s of one node.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload kitti120k|dense2m|cnn] [--scans B] [--points P]
+                    [--workload kitti120k|dense2m|cnn|onecell|uniform80] [--scans B] [--points P]
 
 A "step" is one pass of the hot path over one batch of synthetic scans; every rank owns its own batch
 (weak scaling, no data-path collective -- SURVEY 8e).
@@ -47,6 +47,9 @@ WORKLOADS = {
     "kitti120k": (4096, 120000, 64, 16, "synthetic 64-beam {P}-point scans, batch {B} per GPU (BASELINE configs[2])"),
     "dense2m": (64, 2097152, 128, 4, "synthetic 128-beam dense {P}-point scans, batch {B} per GPU, K1 build + K3 "
                                       "inverse (BASELINE configs[4])"),
+    "onecell": (4096, 120000, 1, 0, "adversarial: all {P} points of a scan in ONE cell, batch {B} per GPU (SURVEY 8d)"),
+    "uniform80": (4096, 120000, 1, 0, "adversarial: {P} points uniform over the 80 m disc (94 % clamp into the last ring), "
+                                       "batch {B} per GPU (SURVEY 8d)"),
     "cnn": (1024, 120000, 64, 16, "synthetic 64-beam {P}-point scans, batch {B} per GPU, K1 + K4 -> TinyCNN "
                                    "(tinycnn_best.pth) -> masks (BASELINE configs[3])"),
 }
@@ -148,12 +151,15 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    from distropointclouds_b200.synth import synth_scan
+    from distropointclouds_b200.synth import adversarial_scan, synth_scan
     B, Pn, beams, n_base, desc = workload_cfg(args)
     cores = orc.max_threads()
     # ~256 scans of 120k points per step (~0.1 s on 16 threads); the same number of points for the dense workload
     sample = max(cores, min(B, int(256 * 120000 / Pn)))
-    base = [synth_scan(i, Pn, beams) for i in range(min(n_base, 4))]
+    if args.workload in ("onecell", "uniform80"):
+        base = [adversarial_scan(args.workload, i, Pn) for i in range(4)]
+    else:
+        base = [synth_scan(i, Pn, beams) for i in range(min(n_base, 4))]
     pts = np.concatenate([base[i % len(base)] for i in range(sample)])
     offs = np.arange(sample + 1, dtype=np.int64) * len(base[0])
     p = orc.Params(R, S, MAXLEN)
@@ -191,7 +197,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from distropointclouds_b200.engine import Engine, ScanContextParams
-    from distropointclouds_b200.synth import synth_batch_device
+    from distropointclouds_b200.synth import adversarial_batch_device, synth_batch_device
 
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -212,7 +218,10 @@ def run_ours(args):
     B, Pn, beams, n_base, desc = workload_cfg(args)
     wl = args.workload
 
-    pts = synth_batch_device(B, Pn, beams, seed=rank, n_base=n_base, device=str(dev))   # (B, P, 4) resident in HBM
+    if wl in ("onecell", "uniform80"):
+        pts = adversarial_batch_device(wl, B, Pn, seed=rank, device=str(dev))
+    else:
+        pts = synth_batch_device(B, Pn, beams, seed=rank, n_base=n_base, device=str(dev))   # (B, P, 4) resident in HBM
     Pn = pts.shape[1]
     offs = np.arange(B + 1, dtype=np.int64) * Pn
     out = torch.empty((B, R, S), dtype=torch.float32, device=dev)
@@ -292,7 +301,7 @@ def run_ours(args):
         h_pts = eng.pinned_empty((B * Pn, 4), np.float32)
         torch.from_numpy(h_pts).copy_(pts.view(-1, 4))
         torch.cuda.synchronize(dev)
-        if wl == "kitti120k":
+        if wl in ("kitti120k", "onecell", "uniform80"):
             h_out = eng.pinned_empty((B, R, S), np.float32)
             d2h = B * R * S * 4
 

@@ -422,13 +422,14 @@ struct SmemRows {
     uint32_t base;   // shared-window address of the resident rows
     int lim;         // cells below lim are resident rows 0 .. ns-2            (0 when nothing is resident)
     int last;        // first cell of the clamp ring, kept in resident row ns-1 (INT_MAX when nothing is)
+    int shift;       // lim - last: clamp-ring cell -> resident row ns-1 (sc_update only)
 };
 
 template <bool FAST, int VARIANT, bool FULL, bool DEF = false, bool SMEM = false>
 __device__ __forceinline__ void st_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v,
                                          uint32_t *__restrict__ grid, unsigned &n_clamped,
                                          unsigned long long *__restrict__ stats, int scan, uint64_t key_policy = 0,
-                                         const SmemRows sm = SmemRows{0u, 0, 0x7fffffff})
+                                         const SmemRows sm = SmemRows{0u, 0, 0x7fffffff, 0})
 {
     int ring = 0, sector = 0;
     bool beyond = false, ok = false;
@@ -663,6 +664,9 @@ k1_stream(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets,
 // 128-bit streaming stores), re-zeroes it and moves on.  There is no synchronisation between CTAs at all;
 // HBM sees each point once and each output cell once.
 constexpr int SC_THREADS = 1024;
+#ifndef SC_TOUCH
+#define SC_TOUCH 0                    // 1: touched-segment flags for the L2-row decode (measured: slower, see r1_notes.md)
+#endif
 #ifndef SC_DU
 #define SC_DU 4                       // 128-bit L2 loads in flight per thread in the decode
 #endif
@@ -701,27 +705,48 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 }
 
 // fold one binned point into the key grid: resident rows -> LDS pre-check + ATOMS.MAX, other rows -> RED.MAX (L2)
-template <bool FULL>
-__device__ __forceinline__ void sc_update(const float zv, const int cell, uint32_t *__restrict__ grid, const SmemRows sm)
+// The L2 rows of a scan are sparse (5-25 % of their cells ever see a point), yet the decode has to read every
+// key back through a ~1 us round trip.  TOUCH: remember which 16-cell segments received a RED (one byte flag per
+// segment in shared memory, plain store), so that the decode reads -- and re-zeroes -- only those.
+constexpr int SC_SEG_SHIFT = 4;                               // 16 cells = 64 B = 4 x 128-bit per segment
+// The flags sit right below the resident rows, one byte per segment of the WHOLE grid and indexed by the
+// absolute cell number, so the hot path needs no extra base register: flag(cell) = rows_base - bytes + (cell >> 4).
+__host__ __device__ constexpr uint32_t sc_flag_bytes(int cells) { return ((uint32_t)(cells >> SC_SEG_SHIFT) + 1u + 127u) & ~127u; }
+
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <bool FULL, bool TOUCH>
+__device__ __forceinline__ void sc_update(const float zv, const int cell, uint32_t *__restrict__ grid, const SmemRows sm,
+                                          const uint32_t flag_bytes)
 {
     const uint32_t u = __float_as_uint(zv);
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
     if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
     if (cell < sm.lim || cell >= sm.last) {
-        const int local = cell < sm.lim ? cell : cell - sm.last + sm.lim;       // clamp ring -> row ns-1
+        const int local = cell < sm.lim ? cell : cell + sm.shift;               // clamp ring -> row ns-1
         const uint32_t addr = sm.base + (uint32_t)local * 4u;
         if (key > lds_u32(addr)) reds_max_u32(addr, key);   // most points are not a new maximum
         return;
     }
     red_max_global(grid + cell, key);
+    if constexpr (TOUCH) sts_u8(sm.base - flag_bytes + (uint32_t)(cell >> SC_SEG_SHIFT), 1u);
 }
 
 // exact chain for one queued point (entry address of this lane); returns 1 if the point was clamped into the last ring
-template <int VARIANT, bool FULL>
+template <int VARIANT, bool FULL, bool TOUCH>
 __device__ __noinline__ unsigned sc_exact_queued(uint32_t qaddr, const ExactArgs *__restrict__ ea,
                                                  uint32_t *__restrict__ grid, uint32_t sm_base, int sm_lim, int sm_last,
-                                                 unsigned long long *__restrict__ st)
+                                                 uint32_t flag_bytes, unsigned long long *__restrict__ st)
 {
     const float x = lds_f32(qaddr), y = lds_f32(qaddr + SCQ_CAP * 4), z = lds_f32(qaddr + SCQ_CAP * 8);
     const uint2 b = hg_bin_exact<VARIANT, FULL>(x, y, z, ea);
@@ -733,16 +758,16 @@ __device__ __noinline__ unsigned sc_exact_queued(uint32_t qaddr, const ExactArgs
         if (status == dsc::PT_OUT_OF_RANGE) atomicAdd(st + 4, 1ull);
     }
     if (status > dsc::PT_CLAMPED) return 0u;
-    sc_update<FULL>(__uint_as_float(b.y), cell, grid, SmemRows{sm_base, sm_lim, sm_last});
+    sc_update<FULL, TOUCH>(__uint_as_float(b.y), cell, grid, SmemRows{sm_base, sm_lim, sm_last, sm_lim - sm_last}, flag_bytes);
     return status == dsc::PT_CLAMPED ? 1u : 0u;
 }
 
 // One point per lane, called warp-uniformly (`active` masks lanes past the end of the item).
-template <int VARIANT, bool FULL, bool DEF>
+template <int VARIANT, bool FULL, bool DEF, bool TOUCH>
 __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v, const bool active,
                                          uint32_t *__restrict__ grid, unsigned &n_clamped,
                                          unsigned long long *__restrict__ st, const SmemRows sm,
-                                         const uint32_t queue, unsigned &qcount)
+                                         const uint32_t queue, unsigned &qcount, const uint32_t flag_bytes)
 {
     int ring, sector;
     bool beyond;
@@ -754,7 +779,7 @@ __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea,
         } else {
             if (VARIANT == 0) n_clamped += beyond;
             const int S = DEF ? dsc::defgrid::S : cfg.S;
-            sc_update<FULL>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, grid, sm);
+            sc_update<FULL, TOUCH>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, grid, sm, flag_bytes);
         }
     }
     const unsigned m = __ballot_sync(0xffffffffu, active && !ok);
@@ -770,23 +795,23 @@ __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea,
         if (qcount >= 32u) {
             qcount -= 32u;
             __syncwarp();
-            n_clamped += sc_exact_queued<VARIANT, FULL>(queue + (qcount + lane) * 4u, ea, grid, sm.base, sm.lim, sm.last, st);
+            n_clamped += sc_exact_queued<VARIANT, FULL, TOUCH>(queue + (qcount + lane) * 4u, ea, grid, sm.base, sm.lim, sm.last, flag_bytes, st);
             __syncwarp();
         }
     }
 }
 
 // end of item: the queue's remaining entries (fewer than 32)
-template <int VARIANT, bool FULL>
+template <int VARIANT, bool FULL, bool TOUCH>
 __device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *__restrict__ grid, unsigned &n_clamped,
                                          unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t queue,
-                                         unsigned &qcount)
+                                         unsigned &qcount, const uint32_t flag_bytes)
 {
     if (qcount) {
         const unsigned lane = threadIdx.x & 31u;
         __syncwarp();
         if (lane < qcount)
-            n_clamped += sc_exact_queued<VARIANT, FULL>(queue + lane * 4u, ea, grid, sm.base, sm.lim, sm.last, st);
+            n_clamped += sc_exact_queued<VARIANT, FULL, TOUCH>(queue + lane * 4u, ea, grid, sm.base, sm.lim, sm.last, flag_bytes, st);
         __syncwarp();
         qcount = 0;
     }
@@ -823,7 +848,7 @@ template <bool SPLIT, int NT, int DU = 4>
 __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid,
                                                float *__restrict__ out_scan, int ns, int R, int S, int scan, int parts,
                                                unsigned int *__restrict__ done, int *s_last,
-                                               unsigned int *__restrict__ reset = nullptr)
+                                               unsigned int *__restrict__ reset = nullptr, const uint32_t flags = 0u)
 {
     const int tid = threadIdx.x;
     const int rowvec = S >> 2;
@@ -895,24 +920,57 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
             const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
             uint4 *kz = reinterpret_cast<uint4 *>(grid);
             const int lo = (ns > 0 ? ns - 1 : 0) * rowvec, hi = (ns > 0 ? R - 1 : R) * rowvec;
-            for (int i0 = lo + tid; i0 < hi; i0 += NT * DU) {
-                uint4 q[DU];
+            if (flags) {
+                // only the segments that received a RED are read back (and re-zeroed); the rest is written as zeros
+                for (int i0 = lo + tid; i0 < hi; i0 += NT * DU) {
+                    uint4 q[DU];
+                    bool t[DU];
 #pragma unroll
-                for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * NT;
-                    if (i < hi) q[d] = __ldcg(kq + i);
+                    for (int d = 0; d < DU; ++d) {
+                        const int i = i0 + d * NT;
+                        t[d] = i < hi && lds_u8(flags + (uint32_t)(i >> (SC_SEG_SHIFT - 2))) != 0u;
+                        if (t[d]) q[d] = __ldcg(kq + i);
+                    }
+#pragma unroll
+                    for (int d = 0; d < DU; ++d) {
+                        const int i = i0 + d * NT;
+                        if (i < hi) {
+                            float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (t[d]) {
+                                f.x = dsc::key_to_float(q[d].x);
+                                f.y = dsc::key_to_float(q[d].y);
+                                f.z = dsc::key_to_float(q[d].z);
+                                f.w = dsc::key_to_float(q[d].w);
+                                __stcg(kz + i, make_uint4(0, 0, 0, 0));
+                            }
+                            __stcs(oq + i, f);
+                        }
+                    }
                 }
+                __syncthreads();                 // every flag has been read ...
+                const int nseg4 = (int)(sc_flag_bytes(R * S) >> 2);                      // flags, in 32-bit words
+                for (int i = tid; i < nseg4; i += NT)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flags + (uint32_t)i * 4u), "r"(0u) : "memory");
+            } else {
+                for (int i0 = lo + tid; i0 < hi; i0 += NT * DU) {
+                    uint4 q[DU];
 #pragma unroll
-                for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * NT;
-                    if (i < hi) {
-                        float4 f;
-                        f.x = dsc::key_to_float(q[d].x);
-                        f.y = dsc::key_to_float(q[d].y);
-                        f.z = dsc::key_to_float(q[d].z);
-                        f.w = dsc::key_to_float(q[d].w);
-                        __stcs(oq + i, f);
-                        __stcg(kz + i, make_uint4(0, 0, 0, 0));
+                    for (int d = 0; d < DU; ++d) {
+                        const int i = i0 + d * NT;
+                        if (i < hi) q[d] = __ldcg(kq + i);
+                    }
+#pragma unroll
+                    for (int d = 0; d < DU; ++d) {
+                        const int i = i0 + d * NT;
+                        if (i < hi) {
+                            float4 f;
+                            f.x = dsc::key_to_float(q[d].x);
+                            f.y = dsc::key_to_float(q[d].y);
+                            f.z = dsc::key_to_float(q[d].z);
+                            f.w = dsc::key_to_float(q[d].w);
+                            __stcs(oq + i, f);
+                            __stcg(kz + i, make_uint4(0, 0, 0, 0));
+                        }
                     }
                 }
             }
@@ -922,6 +980,8 @@ __device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uin
     }
 }
 
+// (A flavour with the resident-row count as a template constant -- row-placement tests and clamp-row shift as
+// immediates -- was measured 10 % SLOWER than this one, which takes `ns` at run time: profiles/r1_notes.md.)
 template <bool FAST, int VARIANT, bool FULL, int U, int NT, bool DEF, bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
@@ -933,7 +993,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     // per-warp chunk counters, 8 decode loads in flight) spilled inside the loop and lost 15-40 %
     // (profiles/r1_notes.md).
     constexpr int STEP = NT * U;
-    extern __shared__ __align__(16) uint32_t srows[];          // [ns ring rows of keys][per-warp exact-path queues]
+    extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ int s_next[2];
     __shared__ int s_last;
     __shared__ ExactArgs s_ea;
@@ -943,14 +1003,18 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int rowvec = S >> 2;                   // host guarantees S % 4 == 0
     uint32_t *grid = SPLIT ? nullptr : keys + (size_t)blockIdx.x * cells;
     const uint64_t pol_stream = l2_policy_evict_first();
+    // dynamic shared memory: [touched-segment flags (TOUCH only)][ns ring rows of keys][per-warp exact-path queues]
+    constexpr bool TOUCH = SC_TOUCH && FAST && !SPLIT;       // whole-scan items of the screened kernels
+    const uint32_t flag_bytes = TOUCH ? sc_flag_bytes(cells) : 0u;
+    uint32_t *const srows = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem_raw) + flag_bytes);
     SmemRows sm;
     sm.base = (uint32_t)__cvta_generic_to_shared(srows);
     sm.lim = ns > 0 ? (ns - 1) * S : 0;
     sm.last = ns > 0 ? (R - 1) * S : 0x7fffffff;
-    // per-warp queue of points waiting for the exact chain, behind the resident rows
+    sm.shift = sm.lim - sm.last;
     const uint32_t queue = sm.base + (uint32_t)ns * (uint32_t)S * 4u + (uint32_t)(tid >> 5) * SCQ_WARP_BYTES;
     unsigned qcount = 0;
-    for (int i = tid; i < ns * rowvec; i += NT) reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (int)(flag_bytes >> 4) + ns * rowvec; i += NT) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         fill_exact_args(&s_ea, cfg);
         s_next[0] = (int)atomicAdd(cursor, 1u);
@@ -975,7 +1039,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 #define SC_LD(ptr) ld_stream_f4_hint((ptr), pol_stream)
 #define SC_PT(v, act)                                                                                           \
     do {                                                                                                        \
-        if constexpr (FAST) sc_point<VARIANT, FULL, DEF>(cfg, &s_ea, (v), (act), grid, n_clamped, st, sm, queue, qcount); \
+        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, TOUCH>(cfg, &s_ea, (v), (act), grid, n_clamped, st, sm, queue, qcount, flag_bytes); \
         else if (act) st_point<false, VARIANT, FULL, DEF, true>(cfg, &s_ea, (v), grid, n_clamped, stats, scan, 0, sm);   \
     } while (0)
         if (nfull > 0) {
@@ -1007,7 +1071,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             if (act) v = SC_LD(s4 + i0 + tid);
             SC_PT(v, act);
         }
-        if constexpr (FAST) sc_drain<VARIANT, FULL>(&s_ea, grid, n_clamped, st, sm, queue, qcount);
+        if constexpr (FAST) sc_drain<VARIANT, FULL, TOUCH>(&s_ea, grid, n_clamped, st, sm, queue, qcount, flag_bytes);
 #undef SC_LD
 #undef SC_PT
         if (stats) {
@@ -1015,7 +1079,8 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
             if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
         }
-        sc_finish_item<SPLIT, NT, SC_DU>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last);
+        sc_finish_item<SPLIT, NT, SC_DU>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last,
+                                         nullptr, TOUCH ? sm.base - flag_bytes : 0u);
         par ^= 1;
         item = s_next[par];                      // published by the barriers of sc_finish_item
     }
@@ -1255,6 +1320,69 @@ k4_apply(const float *__restrict__ grids, int64_t cells, const uint32_t *__restr
     }
 }
 
+// K4, one pass over HBM: a persistent CTA owns one grid at a time -- pass 1 reads it (128-bit loads) and reduces
+// min / max, pass 2 re-reads it from L2 (460 KB per CTA, 68 MB chip-wide: resident) and writes the normalised
+// grid with streaming stores.  HBM sees each grid once in and once out: the algorithmic 2 * 4 * R * S bytes.
+constexpr int K4_THREADS = 1024;
+
+__global__ void __launch_bounds__(K4_THREADS, 1)
+k4_fused(const float *__restrict__ grids, int n, int nvec, float *__restrict__ out)
+{
+    __shared__ uint32_t s_lo[32], s_hi[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int g = blockIdx.x; g < n; g += gridDim.x) {
+        const float4 *p = reinterpret_cast<const float4 *>(grids) + (size_t)g * nvec;
+        float4 *o = reinterpret_cast<float4 *>(out) + (size_t)g * nvec;
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        constexpr int UN = 4;
+        for (int i0 = tid; i0 < nvec; i0 += K4_THREADS * UN) {
+            float4 v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (i0 + u * K4_THREADS < nvec) v[u] = __ldcg(p + i0 + u * K4_THREADS);
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (i0 + u * K4_THREADS < nvec) {
+                    const uint32_t a = dsc::float_to_key(v[u].x), b = dsc::float_to_key(v[u].y);
+                    const uint32_t c = dsc::float_to_key(v[u].z), d = dsc::float_to_key(v[u].w);
+                    lo = min(min(lo, min(a, b)), min(c, d));
+                    hi = max(max(hi, max(a, b)), max(c, d));
+                }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_lo[w] = lo; s_hi[w] = hi; }
+        __syncthreads();
+        lo = s_lo[lane];
+        hi = s_hi[lane];
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        __syncthreads();                         // s_lo / s_hi are rewritten by the next grid
+        const float mn = key_to_float_raw(lo), mx = key_to_float_raw(hi);
+        const bool scale = mx > mn;
+        // (mx - mn) is a Python-float (f64) subtraction in the reference, then a weak f32 scalar
+        const float dd = (float)__dsub_rn((double)mx, (double)mn);
+        for (int i0 = tid; i0 < nvec; i0 += K4_THREADS * UN) {
+            float4 v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (i0 + u * K4_THREADS < nvec) v[u] = __ldcg(p + i0 + u * K4_THREADS);
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (i0 + u * K4_THREADS < nvec) {
+                    float4 r = v[u];
+                    if (scale) {
+                        r.x = __fdiv_rn(__fsub_rn(r.x, mn), dd);
+                        r.y = __fdiv_rn(__fsub_rn(r.y, mn), dd);
+                        r.z = __fdiv_rn(__fsub_rn(r.z, mn), dd);
+                        r.w = __fdiv_rn(__fsub_rn(r.w, mn), dd);
+                    }
+                    __stcs(o + i0 + u * K4_THREADS, r);
+                }
+        }
+    }
+}
+
 }  // namespace
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -1285,6 +1413,11 @@ static int normalize_device(dsc_ctx *ctx, const float *grids, int n, int64_t cel
                             cudaStream_t st)
 {
     if (n <= 0) return DSC_OK;
+    if ((cells & 3) == 0 && cells / 4 < 0x7fffffff && ((((uintptr_t)grids) | ((uintptr_t)out)) & 15) == 0) {
+        const int ctas = n < ctx->sm_count ? n : ctx->sm_count;
+        k4_fused<<<ctas, K4_THREADS, 0, st>>>(grids, n, (int)(cells / 4), out);
+        return dsc_check_launch(ctx, "k4_fused");
+    }
     if ((size_t)n > ctx->minmax_cap) {
         if (ctx->minmax) cudaFree(ctx->minmax);
         ctx->minmax = nullptr;
@@ -1464,12 +1597,15 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         const size_t sc_budget = split ? ctx->smem_optin
                                        : (size_t)(nthreads < 1024 ? 196 : 164) * 1024 - 1024 - 256 - q_bytes;
         const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
-        int ns = (int)((sc_budget < sc_max ? sc_budget : sc_max) / row_bytes);
-        if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                     // A/B override
-        if ((size_t)ns * row_bytes > sc_max) ns = (int)(sc_max / row_bytes);
+        // touched-segment flags (whole-scan items of the screened kernels): one byte per 16 cells of the grid
+        const size_t f_bytes = (SC_TOUCH && cfg.fast_ok && !split) ? sc_flag_bytes((int)cells) : 0;
+        const size_t lim_bytes = (sc_budget < sc_max ? sc_budget : sc_max) - f_bytes;
+        int ns = (int)(lim_bytes / row_bytes);
+        if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                      // A/B override
+        if ((size_t)ns * row_bytes > sc_max - f_bytes) ns = (int)((sc_max - f_bytes) / row_bytes);
         if (ns > p->num_ring) ns = p->num_ring;
         if (ns < 2) ns = 0;
-        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
+        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes + f_bytes;
 #define SC_LAUNCH4(F, V, H, U, NT, D, SP)                                                                       \
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP>,                                      \
@@ -1485,7 +1621,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     do {                                                                                                        \
         if (shape == 1) SC_LAUNCH3(true, V, H, 3, 1024, true);                                                  \
         else if (shape == 2) SC_LAUNCH3(true, V, H, 2, 1024, true);                                             \
-        else SC_LAUNCH3(true, V, H, 3, 768, true);                                                             \
+        else SC_LAUNCH3(true, V, H, 3, 768, true);                                                              \
     } while (0)
         if (cfg.fast_ok && defgrid) {
             if (p->variant == 0) { if (full) SC_LAUNCH_DEF(0, true); else SC_LAUNCH_DEF(0, false); }

@@ -63,3 +63,48 @@ def synth_batch_device(n_scans: int, n_points: int = 120000, beams: int = 64, se
         out[s0:s1, :, 2] = b[:, :, 2].to(torch.float32)
         out[s0:s1, :, 3] = b[:, :, 3].to(torch.float32)
     return out
+
+
+def adversarial_batch_device(kind: str, n_scans: int, n_points: int = 120000, seed: int = 0, device: str = "cuda"):
+    """The two adversarial distributions of SURVEY 8(d), generated on the device (workload generation, outside any
+    timed region):  'onecell'   every point of a scan falls into ONE grid cell (maximum atomic contention);
+                    'uniform80' uniform over the 80 m disc (~94 % of the points beyond 20 m: clamp-ring pile-up)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(20251018 + 7919 * seed + (1 if kind == "onecell" else 2))
+    out = torch.empty((n_scans, n_points, 4), dtype=torch.float32, device=device)
+    for s0 in range(0, n_scans, 256):
+        s1 = min(n_scans, s0 + 256)
+        shape = (s1 - s0, n_points)
+        u = torch.rand(shape, generator=g, device=device, dtype=torch.float64)
+        v = torch.rand(shape, generator=g, device=device, dtype=torch.float64)
+        w = torch.rand(shape, generator=g, device=device, dtype=torch.float64)
+        if kind == "onecell":
+            # cell (ring 40, sector 90): r in [5.0, 5.125), theta in [45.0, 45.5) degrees, well inside
+            r = 5.02 + 0.08 * u
+            th = np.deg2rad(45.05) + np.deg2rad(0.4) * v
+        elif kind == "uniform80":
+            r = 80.0 * torch.sqrt(u)
+            th = 2 * np.pi * v
+        else:
+            raise ValueError(kind)
+        out[s0:s1, :, 0] = (torch.round(r * torch.cos(th) * 1000) / 1000).to(torch.float32)
+        out[s0:s1, :, 1] = (torch.round(r * torch.sin(th) * 1000) / 1000).to(torch.float32)
+        out[s0:s1, :, 2] = (torch.round((w * 3.0 - 2.0) * 1000) / 1000).to(torch.float32)
+        out[s0:s1, :, 3] = 0.5
+    return out
+
+
+def adversarial_scan(kind: str, seed: int, n: int = 120000):
+    """Host (NumPy) flavour of the adversarial distributions, for the CPU arm."""
+    rng = np.random.default_rng(20251018 + 7919 * seed + (1 if kind == "onecell" else 2))
+    u, v, w = rng.random(n), rng.random(n), rng.random(n)
+    if kind == "onecell":
+        r, th = 5.02 + 0.08 * u, np.deg2rad(45.05) + np.deg2rad(0.4) * v
+    elif kind == "uniform80":
+        r, th = 80.0 * np.sqrt(u), 2 * np.pi * v
+    else:
+        raise ValueError(kind)
+    pts = np.stack([np.round(r * np.cos(th) * 1000) / 1000, np.round(r * np.sin(th) * 1000) / 1000,
+                    np.round((w * 3.0 - 2.0) * 1000) / 1000, np.full(n, 0.5)], axis=1)
+    return pts.astype(np.float32)
