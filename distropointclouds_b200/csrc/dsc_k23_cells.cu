@@ -117,6 +117,159 @@ k3_rows(const float *__restrict__ grids, int n_grids, int R, int S, int full_hei
     if (!WRITE && lane == 0) row_counts[row] = count;
 }
 
+// ---- K3, single pass over HBM ---------------------------------------------------------------------
+// Persistent CTAs take grids in ticket order.  Pass A counts the kept cells of each ring row (the grid comes in
+// from HBM and stays in L2: 460 KB per CTA), a CTA-wide scan turns the counts into row offsets, the grid's base
+// offset comes from a decoupled look-back over the totals of the grids before it (they are owned by CTAs that
+// drew earlier tickets and are running, so the wait terminates), pass C re-reads the rows from L2 and writes the
+// points in row-major order.  HBM sees each grid once and each output byte once.
+constexpr int K3F_THREADS = 1024;
+constexpr int K3F_CTAS_PER_SM = 1;                             // 2 x 512 threads measured 4 % slower
+constexpr int K3F_WARPS = K3F_THREADS / 32;
+constexpr int K3F_MAXR = 2048;                                 // rows per grid the shared-memory scan can hold
+constexpr int K3F_MAXROUNDS = 8;                               // 128 cells per warp round: S <= 1024
+constexpr int K3F_STAGE_BYTES = 128 * 24 + 128 * 4;            // per-warp output staging
+constexpr unsigned long long K3F_AGG = 1ull << 62, K3F_PFX = 2ull << 62, K3F_VAL = (1ull << 62) - 1;
+
+// One ring row per warp at a time, read as 128-bit vectors with every load of the row in flight at once
+// (ROUNDS x 512 B per warp); lane l of round k holds cells 4 * (32 k + l) .. + 3.
+template <int ROUNDS>
+__global__ void __launch_bounds__(K3F_THREADS, K3F_CTAS_PER_SM)
+k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_height, float offset_f,
+         const double *__restrict__ rcs, const double *__restrict__ cosT, const double *__restrict__ sinT,
+         unsigned int *__restrict__ ticket, unsigned long long *__restrict__ status,
+         int64_t *__restrict__ item_offsets, double *__restrict__ pts_out, int32_t *__restrict__ ids_out, int64_t cap)
+{
+    __shared__ int s_cnt[K3F_MAXR];
+    __shared__ int s_g;
+    __shared__ long long s_base;
+    extern __shared__ __align__(16) double k3_stage[];         // per warp: 128 x 3 doubles, then 128 ints
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double *dbuf = k3_stage + (size_t)w * (K3F_STAGE_BYTES / 8);
+    int *ibuf = reinterpret_cast<int *>(dbuf + 384);
+    const int rowvec = S >> 2;
+    const unsigned lt = (1u << lane) - 1u;
+    for (;;) {
+        if (tid == 0) s_g = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int g = s_g;
+        if (g >= n_grids) break;
+        const float4 *gp = reinterpret_cast<const float4 *>(grids + (size_t)g * R * S);
+        // ---- pass A: kept cells per row ----
+        for (int r = w; r < R; r += K3F_WARPS) {
+            const float4 *row = gp + (size_t)r * rowvec;
+            float4 v[ROUNDS];
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {
+                const int i = k * 32 + lane;
+                v[k] = i < rowvec ? __ldcg(row + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            int count = 0;
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {
+                if (full_height) count += (v[k].x != 0.0f) + (v[k].y != 0.0f) + (v[k].z != 0.0f) + (v[k].w != 0.0f);
+                else count += (v[k].x > 0.0f) + (v[k].y > 0.0f) + (v[k].z > 0.0f) + (v[k].w > 0.0f);
+            }
+            count = __reduce_add_sync(0xffffffffu, count);
+            if (lane == 0) s_cnt[r] = count;
+        }
+        __syncthreads();
+        // ---- exclusive scan of the row counts (warp 0), look-back for the grid's base (thread 0) ----
+        if (w == 0) {
+            int run = 0;
+            for (int r0 = 0; r0 < R; r0 += 32) {
+                const int r = r0 + lane;
+                const int c = r < R ? s_cnt[r] : 0;
+                int inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                if (r < R) s_cnt[r] = run + inc - c;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) {
+                const unsigned long long total = (unsigned long long)run;
+                volatile unsigned long long *stv = status;
+                long long base = 0;
+                if (g == 0) {
+                    stv[0] = K3F_PFX | total;
+                } else {
+                    stv[g] = K3F_AGG | total;
+                    __threadfence();
+                    int q = g - 1;
+                    for (;;) {
+                        const unsigned long long sv = stv[q];
+                        if (sv == 0ull) { __nanosleep(40); continue; }
+                        base += (long long)(sv & K3F_VAL);
+                        if (sv & K3F_PFX) break;
+                        --q;
+                    }
+                    stv[g] = K3F_PFX | ((unsigned long long)base + total);
+                }
+                item_offsets[g] = base;
+                if (g == n_grids - 1) item_offsets[n_grids] = base + (long long)total;
+                s_base = base;
+            }
+        }
+        __syncthreads();
+        // ---- pass C: write the points in row-major order (rows come from L2) ----
+        const long long gbase = s_base;
+        for (int r = w; r < R; r += K3F_WARPS) {
+            const float4 *row = gp + (size_t)r * rowvec;
+            const double rc = rcs[r];
+            float4 v[ROUNDS];
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {
+                const int i = k * 32 + lane;
+                v[k] = i < rowvec ? __ldcg(row + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            int64_t base = gbase + s_cnt[r];
+#pragma unroll
+            for (int k = 0; k < ROUNDS; ++k) {
+                const float zc[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+                bool kp[4];
+                unsigned bal[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    kp[c] = full_height ? (zc[c] != 0.0f) : (zc[c] > 0.0f);
+                    bal[c] = __ballot_sync(0xffffffffu, kp[c]);
+                }
+                const int m = __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+                if (m == 0) continue;
+                // kept cells of lower lanes come first, then this lane's lower components; the round's points are
+                // staged in the warp's shared-memory buffer so that they leave as contiguous 256-byte stores
+                int rank = __popc(bal[0] & lt) + __popc(bal[1] & lt) + __popc(bal[2] & lt) + __popc(bal[3] & lt);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (kp[c]) {
+                        const int j = 4 * (k * 32 + lane) + c;
+                        dbuf[3 * rank + 0] = __dmul_rn(rc, cosT[j]);   // :58  X = r * cos(theta)
+                        dbuf[3 * rank + 1] = __dmul_rn(rc, sinT[j]);   // :59
+                        // :66 the offset is removed in the grid's dtype (float32 .npy grids)
+                        dbuf[3 * rank + 2] = full_height ? (double)zc[c] : (double)__fsub_rn(zc[c], offset_f);
+                        ibuf[rank] = r * S + j;                        // :74
+                        ++rank;
+                    }
+                }
+                __syncwarp();
+                for (int t = lane; t < 3 * m; t += 32) {
+                    const int64_t o3 = 3 * base + t;
+                    if (o3 < 3 * cap) pts_out[o3] = dbuf[t];
+                }
+                for (int t = lane; t < m; t += 32) {
+                    const int64_t o = base + t;
+                    if (o < cap) ids_out[o] = ibuf[t];
+                }
+                __syncwarp();
+                base += m;
+            }
+        }
+        __syncthreads();                         // s_cnt / s_g are rewritten by the next grid
+    }
+}
+
 // ---- two-level exclusive scan: rows within an item, then items ---------------------------------
 // level 1: one warp per item: row_offsets[item][r] = sum_{q<r} counts, item_totals[item] = sum
 __global__ void __launch_bounds__(ROW_WARPS * 32)
@@ -346,6 +499,27 @@ extern "C" int dsc_reconstruct_batch(dsc_ctx *ctx, const float *grids, int n_gri
     if (n_grids == 0) {
         DSC_CUDA(ctx, cudaMemsetAsync(item_offsets, 0, 8, st));
     } else {
+        const int rounds = (S / 4 + 31) / 32;
+        if (R <= K3F_MAXR && (S & 3) == 0 && rounds <= K3F_MAXROUNDS && (((uintptr_t)d_grids) & 15) == 0) {
+            // single pass: ticket counter + look-back status words live in the (otherwise unused) counts area
+            unsigned int *ticket = (unsigned int *)row_counts;
+            unsigned long long *status = (unsigned long long *)row_offsets;
+            DSC_CUDA(ctx, cudaMemsetAsync(ticket, 0, 16, st));
+            DSC_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)n_grids * 8, st));
+            const int max_ctas = ctx->sm_count * K3F_CTAS_PER_SM;
+            const int ctas = n_grids < max_ctas ? n_grids : max_ctas;   // tickets are drawn by running CTAs only: look-back cannot stall
+            const int k3_smem = K3F_WARPS * K3F_STAGE_BYTES;
+#define K3F_LAUNCH(RN)                                                                                          \
+    DSC_CUDA(ctx, cudaFuncSetAttribute(k3_fused<RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem));    \
+    k3_fused<RN><<<ctas, K3F_THREADS, k3_smem, st>>>(d_grids, n_grids, R, S, full_height, (float)height_offset, ctx->d_rc, \
+                                               ctx->d_cos, ctx->d_sin, ticket, status, item_offsets, d_pts, d_ids, cap)
+            if (rounds <= 2) { K3F_LAUNCH(2); }
+            else if (rounds <= 4) { K3F_LAUNCH(4); }
+            else if (rounds <= 6) { K3F_LAUNCH(6); }
+            else { K3F_LAUNCH(8); }
+#undef K3F_LAUNCH
+            if ((rc = dsc_check_launch(ctx, "k3_fused"))) return rc;
+        } else {
         const unsigned blocks = (unsigned)((n_rows + ROW_WARPS - 1) / ROW_WARPS);
         k3_rows<false><<<blocks, ROW_WARPS * 32, 0, st>>>(d_grids, n_grids, R, S, full_height, (float)height_offset,
                                                           ctx->d_rc, ctx->d_cos, ctx->d_sin, row_counts, nullptr,
@@ -356,6 +530,7 @@ extern "C" int dsc_reconstruct_batch(dsc_ctx *ctx, const float *grids, int n_gri
                                                          ctx->d_rc, ctx->d_cos, ctx->d_sin, row_counts, row_offsets,
                                                          d_pts, d_ids, cap);
         if ((rc = dsc_check_launch(ctx, "k3_rows<write>"))) return rc;
+        }
     }
     if (!host) return DSC_OK;
     DSC_CUDA(ctx, cudaMemcpyAsync(pt_offsets, item_offsets, (size_t)(n_grids + 1) * 8, cudaMemcpyDeviceToHost, st));
