@@ -31,7 +31,7 @@ extern "C" int dsc_create(int device, dsc_ctx **out)
               cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i)
+    for (int i = 0; i < DSC_NBUF && ok; ++i)
         ok = cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
@@ -53,7 +53,7 @@ extern "C" int dsc_destroy(dsc_ctx *ctx)
     if (ctx->work_counter) cudaFree(ctx->work_counter);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < DSC_NBUF; ++i) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
         if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);

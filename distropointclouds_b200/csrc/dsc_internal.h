@@ -9,6 +9,11 @@
 #include "../../include/dsc.h"
 #include "dsc_math.cuh"
 
+// staging buffers of the host-buffer pipeline (H2D of chunk i+2 / i+1, kernels of chunk i, D2H of chunk i-1)
+#ifndef DSC_NBUF
+#define DSC_NBUF 3
+#endif
+
 struct dsc_ctx {
     int device = 0;
     int sm_count = 148;
@@ -46,14 +51,14 @@ struct dsc_ctx {
 
     // host-path pipeline: H2D stream -> kernel stream -> D2H stream, double buffered
     cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
-    void *stage_pts[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[DSC_NBUF] = {}, ev_k[DSC_NBUF] = {}, ev_d2h[DSC_NBUF] = {};
+    void *stage_pts[DSC_NBUF] = {};
     size_t stage_pts_cap = 0;
-    float *stage_out[2] = {nullptr, nullptr};
-    float *stage_norm[2] = {nullptr, nullptr};
-    dsc_scan_stats *stage_stats[2] = {nullptr, nullptr};
-    int64_t *stage_doff[2] = {nullptr, nullptr};   // device offsets per buffer
-    int64_t *stage_hoff[2] = {nullptr, nullptr};   // pinned offsets per buffer
+    float *stage_out[DSC_NBUF] = {};
+    float *stage_norm[DSC_NBUF] = {};
+    dsc_scan_stats *stage_stats[DSC_NBUF] = {};
+    int64_t *stage_doff[DSC_NBUF] = {};   // device offsets per buffer
+    int64_t *stage_hoff[DSC_NBUF] = {};   // pinned offsets per buffer
     size_t stage_scans_cap = 0;
     size_t stage_cells = 0;
 

@@ -1829,7 +1829,7 @@ static int upload_offsets(dsc_ctx *ctx, const int64_t *offsets, int n_scans, cud
 
 static void free_stage(dsc_ctx *ctx)
 {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < DSC_NBUF; ++i) {
         if (ctx->stage_pts[i]) cudaFree(ctx->stage_pts[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
         if (ctx->stage_norm[i]) cudaFree(ctx->stage_norm[i]);
@@ -1882,7 +1882,7 @@ static int build_host(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, con
     if (pts_cap > ctx->stage_pts_cap || scans_cap > ctx->stage_scans_cap || (size_t)cells != ctx->stage_cells) {
         DSC_CUDA(ctx, cudaDeviceSynchronize());
         free_stage(ctx);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < DSC_NBUF; ++i) {
             DSC_CUDA(ctx, cudaMalloc(&ctx->stage_pts[i], pts_cap + 16));
             DSC_CUDA(ctx, cudaMalloc(&ctx->stage_out[i], scans_cap * cells * 4));
             DSC_CUDA(ctx, cudaMalloc(&ctx->stage_norm[i], scans_cap * cells * 4));
@@ -1895,7 +1895,7 @@ static int build_host(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, con
         ctx->stage_cells = (size_t)cells;
     }
     int s0 = 0, buf = 0, rc = DSC_OK;
-    int used[2] = {0, 0};
+    int used[DSC_NBUF] = {};
     while (s0 < n_scans) {
         int s1 = s0;
         size_t bytes = 0;
@@ -1939,7 +1939,7 @@ static int build_host(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, con
         DSC_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[buf], ctx->s_d2h));
         used[buf] = 1;
         s0 = s1;
-        buf ^= 1;
+        buf = buf + 1 == DSC_NBUF ? 0 : buf + 1;
     }
     DSC_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
     DSC_CUDA(ctx, cudaStreamSynchronize(ctx->s_k));

@@ -332,3 +332,78 @@ def test_covered_cells_fixtures(engine, golden_grids, golden_peds, ref_live):
     _, ids = engine.reconstruct_host(g)[0]
     m = engine.covered_mask_host(ids, np.array(cells))
     assert m.dtype == bool and np.array_equal(m, ref_live["covered_000840__mask"])
+
+
+# ---- added with the single-pass K3 / one-pass K4 / split-mode K1 ----------------------------------------------------
+@pytest.mark.parametrize("shape", [(40, 90), (8, 1024), (3, 2000), (200, 36), (160, 722)])
+def test_reconstructor_other_grids_vs_oracle(engine, orc, shape):
+    """Vector path (S % 4 == 0, up to 8 warp rounds per row) and the generic three-kernel path (odd S, very long
+    rows), dense / sparse / empty grids, both height modes -- bit-exact against the oracle."""
+    R, S = shape
+    rng = np.random.default_rng(R * 1000 + S)
+    grids = np.zeros((5, R, S), np.float32)
+    grids[0] = rng.standard_normal((R, S)).astype(np.float32)                         # dense
+    m = rng.random((R, S)) < 0.07
+    grids[1][m] = rng.uniform(-3, 3, m.sum()).astype(np.float32)                      # sparse
+    grids[3][R - 1, S - 1] = 1.5                                                       # one cell, the very last
+    grids[4] = np.where(rng.random((R, S)) < 0.5, rng.uniform(-1, 1, (R, S)), 0).astype(np.float32)
+    for full in (True, False):
+        out = engine.reconstruct_host(grids, R, S, 33.0, full_height=full, height_offset=0.75)
+        for i in range(len(grids)):
+            op, oi = orc.reconstruct(grids[i], R, S, 33.0, full, 0.75)
+            assert np.array_equal(out[i][0], op) and np.array_equal(out[i][1], oi), (shape, full, i)
+
+
+def test_reconstruct_device_capacity_and_offsets(engine, golden_grids):
+    """Device form: CSR offsets on the device, writes clipped at the caller's capacity, many grids (look-back chain)."""
+    import torch
+    g = torch.from_numpy(np.stack([golden_grids[s] for s in SCAN_IDS] * 75)).cuda()      # 300 grids > #SMs
+    n = g.shape[0]
+    counts = np.array([np.count_nonzero(golden_grids[s]) for s in SCAN_IDS] * 75)
+    offs = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    total = int(counts.sum())
+    pts = torch.empty((total, 3), dtype=torch.float64, device="cuda")
+    ids = torch.empty(total, dtype=torch.int32, device="cuda")
+    engine.reconstruct_device(g, offs, pts, ids)
+    torch.cuda.synchronize()
+    assert np.array_equal(offs.cpu().numpy(), np.concatenate([[0], np.cumsum(counts)]))
+    first = engine.reconstruct_host(golden_grids[SCAN_IDS[0]])[0]
+    a, b = int(offs[296]), int(offs[297])
+    assert np.array_equal(pts[a:b].cpu().numpy(), first[0]) and np.array_equal(ids[a:b].cpu().numpy(), first[1])
+    # capacity smaller than the result: offsets still complete, nothing written past the end
+    small = torch.full((1000, 3), -7.0, dtype=torch.float64, device="cuda")
+    guard = torch.full((1000,), -7, dtype=torch.int32, device="cuda")
+    engine.reconstruct_device(g[:2], offs[:3], small[:900], guard[:900])
+    torch.cuda.synchronize()
+    assert int(offs[2]) == int(counts[:2].sum()) and float(small[900:].max()) == -7.0 and int(guard[900:].max()) == -7
+    assert np.array_equal(small[:900].cpu().numpy(), first[0][:900])
+
+
+def test_normalize01_odd_sizes_and_constant_grids(engine, orc):
+    rng = np.random.default_rng(5)
+    for shape in [(3, 7, 9), (2, 160, 720), (5, 1, 4), (1, 33, 100)]:
+        g = rng.standard_normal(shape).astype(np.float32) * 5
+        g[0] = 2.5                                                     # max == min: returned unchanged
+        got = engine.normalize01_host(g)
+        for i in range(shape[0]):
+            assert np.array_equal(got[i], orc.normalize01(g[i])), (shape, i)
+
+
+@pytest.mark.parametrize("item_points", [16384, 50000, 1 << 20])
+def test_split_items_are_invisible(orc, golden_scans, item_points):
+    """K1 cuts big scans / small batches into work items; the grids must not depend on how."""
+    from distropointclouds_b200.engine import Engine
+    rng = np.random.default_rng(11)
+    base = golden_scans["002095"]
+    scans = [base, base[:1], base[:0], np.concatenate([base, golden_scans["000840"], base[::-1]]), base[:70001]]
+    e = Engine(0)
+    try:
+        e.set_option("sc_split", 1)
+        e.set_option("sc_item_points", item_points)
+        got, _, stats = e.build_scans(scans, P())
+    finally:
+        e.close()
+    for i, sc in enumerate(scans):
+        ref, st = orc.sc_build(sc) if len(sc) else (np.zeros((160, 720), np.float32), None)
+        assert np.array_equal(got[i], ref), i
+        assert int(stats[i][0]) == len(sc)
