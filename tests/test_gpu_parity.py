@@ -407,3 +407,36 @@ def test_split_items_are_invisible(orc, golden_scans, item_points):
         ref, st = orc.sc_build(sc) if len(sc) else (np.zeros((160, 720), np.float32), None)
         assert np.array_equal(got[i], ref), i
         assert int(stats[i][0]) == len(sc)
+
+
+def test_full_size_batch_properties(orc):
+    """BASELINE configs[2] at full size (4096 x 120 000 points, device resident, the whole-scan path of K1):
+    a sample of the grids against the oracle, and the whole batch against the same scans pushed through in
+    small batches (split-item path) -- two different kernels paths must agree on every one of the 4096 grids."""
+    import torch
+    from distropointclouds_b200.engine import Engine
+    from distropointclouds_b200.synth import synth_batch_device
+    B, N = 4096, 120000
+    pts = synth_batch_device(B, N, 64, seed=3, device="cuda")
+    N = pts.shape[1]
+    offs = np.arange(B + 1, dtype=np.int64) * N
+    e = Engine(0)
+    try:
+        out = torch.empty((B, 160, 720), dtype=torch.float32, device="cuda")
+        st = torch.zeros((B, 6), dtype=torch.int64, device="cuda")
+        e.build_device(pts, offs, P(), out, None, st)
+        again = torch.empty_like(out)
+        e.build_device(pts, offs, P(), again, None, None)
+        torch.cuda.synchronize()
+        assert torch.equal(out, again)                                           # run-to-run determinism
+        assert int(st[:, 0].min()) == N and int(st[:, 0].max()) == N and int(st[:, 1].sum()) == 0
+        for i in (0, 1, 147, 148, 2047, 4094, 4095):                             # first/last wave, CTA boundaries
+            ref, rst = orc.sc_build(pts[i].cpu().numpy())
+            assert np.array_equal(out[i].cpu().numpy(), ref), i
+            assert int(st[i, 3]) == rst["n_clamped_ring"], i
+        small = torch.empty((64, 160, 720), dtype=torch.float32, device="cuda")
+        for a in range(0, B, 64):                                                # 64 scans per call: split items
+            e.build_device(pts[a:a + 64], offs[: 65], P(), small, None, None)
+            assert torch.equal(small, out[a:a + 64]), a
+    finally:
+        e.close()
