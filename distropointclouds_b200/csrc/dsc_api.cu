@@ -24,6 +24,8 @@ extern "C" int dsc_create(int device, dsc_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = prop.l2CacheSize;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (const char *e = getenv("DSC_K1_IMPL")) ctx->k1_impl = atoi(e);   // debugging / A-B benchmarking only
     if (const char *e = getenv("DSC_SC_LOADER")) ctx->sc_loader = atoi(e);
     if (const char *e = getenv("DSC_SC_CFG")) ctx->sc_cfg = atoi(e);
@@ -78,6 +80,7 @@ extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "k1_impl") && value >= 0 && value <= 4) { ctx->k1_impl = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_smem_rows") && value >= -1 && value <= 65536) { ctx->sc_smem_rows = (int)value; return DSC_OK; }
     if (!strcmp(name, "no_defgrid") && value >= 0 && value <= 1) { ctx->no_defgrid = (int)value; return DSC_OK; }
+    if (!strcmp(name, "l2_persist") && value >= 0 && value <= 1) { ctx->l2_persist = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_loader") && value >= 0 && value <= 1) { ctx->sc_loader = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_split") && value >= -1 && value <= 1) { ctx->sc_split = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_item_points") && value >= 1024 && value <= (1 << 30)) { ctx->sc_item_points = (int)value; return DSC_OK; }

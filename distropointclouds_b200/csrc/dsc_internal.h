@@ -25,6 +25,8 @@ struct dsc_ctx {
     int sc_smem_rows = -1;           // scan kernel: ring rows kept in shared memory (-1 = as many as fit, 0 = none)
     int no_defgrid = 0;              // 1: do not use the default-grid specialisation (A/B runs)
     int sc_cfg = 0;                  // scan kernel launch shape (screened default-grid kernels): 0 = 768 thr x 3 loads, 1 = 1024x3, 2 = 1024x2
+    size_t persist_max = 0, window_max = 0, persist_set = 0;   // L2 persistence limits of the device
+    int l2_persist = 0;              // 1: keep the key slots in the persisting part of L2 during the launch
     int sc_loader = 0;               // scan kernel point loader: 0 = 128-bit register loads, 1-4 = TMA ring shapes (k1_ring)
     int sc_split = -1;               // scan kernel: -1 auto, 0 never split scans into items, 1 always
     int sc_item_points = 131072;     // scan kernel: target points per work item when scans are split

@@ -1001,7 +1001,10 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int R = DEF ? dsc::defgrid::R : cfg.R, S = DEF ? dsc::defgrid::S : cfg.S;
     const int cells = R * S;
     const int rowvec = S >> 2;                   // host guarantees S % 4 == 0
-    uint32_t *grid = SPLIT ? nullptr : keys + (size_t)blockIdx.x * cells;
+    // private L2 slot of this CTA: only the non-resident rows exist in it; the pointer is biased so that it is still
+    // indexed by the absolute cell number
+    uint32_t *grid = SPLIT ? nullptr
+                           : keys + (size_t)blockIdx.x * (size_t)((ns > 0 ? R - ns : R) * S) - (ns > 0 ? (ns - 1) * S : 0);
     const uint64_t pol_stream = l2_policy_evict_first();
     // dynamic shared memory: [touched-segment flags (TOUCH only)][ns ring rows of keys][per-warp exact-path queues]
     constexpr bool TOUCH = SC_TOUCH && FAST && !SPLIT;       // whole-scan items of the screened kernels
@@ -1455,6 +1458,19 @@ static int dsc_reserve_sync(dsc_ctx *ctx, size_t bytes)
     return DSC_OK;
 }
 
+// key scratch (always left zeroed by the kernels that use it)
+static int ensure_keys(dsc_ctx *ctx, size_t need, cudaStream_t st)
+{
+    if (need <= ctx->keys_bytes) return DSC_OK;
+    if (ctx->keys) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->keys); }
+    ctx->keys = nullptr;
+    ctx->keys_bytes = 0;
+    DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
+    ctx->keys_bytes = need;
+    DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
+    return DSC_OK;
+}
+
 // Device-resident batch: pts/out/stats are device pointers, offsets already on the device.
 static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, const int64_t *d_offsets,
                         const int64_t *h_offsets, int n_scans, int stride, float *out, float *out_norm,
@@ -1499,15 +1515,6 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         int ctas = ctx->sm_count;
         const int64_t n_items = split ? split_items : (int64_t)n_scans;
         if (ctas > n_items) ctas = (int)n_items;
-        const size_t need = split ? 0 : (size_t)ctx->sm_count * cells * 4;
-        if (need > ctx->keys_bytes) {
-            if (ctx->keys) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->keys); }
-            ctx->keys = nullptr;
-            ctx->keys_bytes = 0;
-            DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
-            ctx->keys_bytes = need;
-            DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
-        }
         // sync block: [cursor (16 B)] [done[n_scans]] [item_base[n_scans+1] (ragged batches)]
         SplitArgs spa = {nullptr, nullptr, 0, 0};
         size_t sync_bytes = 16;
@@ -1558,6 +1565,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             if (ns > p->num_ring) ns = p->num_ring;
             if (ns < 2) ns = 0;
             const size_t rg_smem = (((size_t)ns * row_bytes + 127) & ~(size_t)127) + ring_bytes;
+            if ((rc = ensure_keys(ctx, split ? 0 : (size_t)ctx->sm_count * cells * 4, st))) return rc;   // full-size slots
 #define RG_LAUNCH3(V, H, U, N, SP)                                                                              \
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_ring<true, V, H, U, N, true, SP>,                                 \
@@ -1606,6 +1614,27 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         if (ns > p->num_ring) ns = p->num_ring;
         if (ns < 2) ns = 0;
         const size_t sc_smem = (size_t)ns * row_bytes + q_bytes + f_bytes;
+        // private key slots (whole-scan items): the non-resident rows of one grid per CTA, L2-resident
+        const size_t slot_bytes = (size_t)(ns > 0 ? p->num_ring - ns : p->num_ring) * row_bytes;
+        const size_t need = split ? 0 : (size_t)ctx->sm_count * slot_bytes;
+        if ((rc = ensure_keys(ctx, need, st))) return rc;
+        // optional: keep the slots in the persisting part of L2 for the duration of the launch
+        cudaStreamAttrValue win;
+        memset(&win, 0, sizeof win);
+        if (ctx->l2_persist && need > 0 && ctx->persist_max > 0) {
+            const size_t want = need < ctx->persist_max ? need : ctx->persist_max;
+            if (ctx->persist_set < want) {
+                DSC_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+                ctx->persist_set = want;
+            }
+            win.accessPolicyWindow.base_ptr = ctx->keys;
+            win.accessPolicyWindow.num_bytes = need < ctx->window_max ? need : ctx->window_max;
+            const double ratio = (double)ctx->persist_set / (double)win.accessPolicyWindow.num_bytes;
+            win.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+            win.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            win.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
+        }
 #define SC_LAUNCH4(F, V, H, U, NT, D, SP)                                                                       \
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP>,                                      \
@@ -1637,6 +1666,10 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
 #undef SC_LAUNCH3
 #undef SC_LAUNCH4
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
+        if (win.accessPolicyWindow.num_bytes) {      // leave the caller's stream as we found it
+            win.accessPolicyWindow.num_bytes = 0;
+            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
+        }
         if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
         return DSC_OK;
     }
