@@ -133,6 +133,15 @@ constexpr unsigned long long K3F_AGG = 1ull << 62, K3F_PFX = 2ull << 62, K3F_VAL
 
 // One ring row per warp at a time, read as 128-bit vectors with every load of the row in flight at once
 // (ROUNDS x 512 B per warp); lane l of round k holds cells 4 * (32 k + l) .. + 3.
+__device__ __forceinline__ float4 k3_ld(const float4 *p, uint64_t pol)
+{
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
 template <int ROUNDS>
 __global__ void __launch_bounds__(K3F_THREADS, K3F_CTAS_PER_SM)
 k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_height, float offset_f,
@@ -149,6 +158,10 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
     int *ibuf = reinterpret_cast<int *>(dbuf + 384);
     const int rowvec = S >> 2;
     const unsigned lt = (1u << lane) - 1u;
+    // pass A parks the grid in L2 (evict last), pass C lets go of it (evict first)
+    uint64_t pol_keep, pol_drop;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
     for (;;) {
         if (tid == 0) s_g = (int)atomicAdd(ticket, 1u);
         __syncthreads();
@@ -162,7 +175,7 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
 #pragma unroll
             for (int k = 0; k < ROUNDS; ++k) {
                 const int i = k * 32 + lane;
-                v[k] = i < rowvec ? __ldcg(row + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                v[k] = i < rowvec ? k3_ld(row + i, pol_keep) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
             int count = 0;
 #pragma unroll
@@ -223,7 +236,7 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
 #pragma unroll
             for (int k = 0; k < ROUNDS; ++k) {
                 const int i = k * 32 + lane;
-                v[k] = i < rowvec ? __ldcg(row + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                v[k] = i < rowvec ? k3_ld(row + i, pol_drop) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
             int64_t base = gbase + s_cnt[r];
 #pragma unroll

@@ -264,7 +264,8 @@ class Engine:
                 continue
             self._check(rc)
             break
-        out = [cells[offs[i]:offs[i + 1]].astype(np.int64) for i in range(nb)]
+        c64 = cells[: int(offs[nb])].astype(np.int64)            # one conversion, then views per box
+        out = [c64[offs[i]:offs[i + 1]] for i in range(nb)]
         return out, mask
 
     # -- K3 ------------------------------------------------------------------------------------
@@ -281,7 +282,8 @@ class Engine:
         self._check(self._lib.dsc_reconstruct_batch(self._h, _ptr(g), n, int(bool(full_height)),
                                                     float(height_offset), _ffi.MEM_HOST, _ptr(offs), _ptr(pts),
                                                     _ptr(ids), cap, None))
-        return [(pts[offs[i]:offs[i + 1]].copy(), ids[offs[i]:offs[i + 1]].copy()) for i in range(n)]
+        # views of the two result buffers (one allocation per call, no per-grid copies)
+        return [(pts[offs[i]:offs[i + 1]], ids[offs[i]:offs[i + 1]]) for i in range(n)]
 
     def reconstruct_device(self, grids, pt_offsets, pts_out, bin_ids_out, num_ring=160, num_sector=720,
                            max_length=20.0, full_height=True, height_offset=2.0, stream: Optional[int] = None):
