@@ -202,25 +202,40 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
                 if (r < R) s_cnt[r] = run + inc - c;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
-            if (lane == 0) {
-                const unsigned long long total = (unsigned long long)run;
-                volatile unsigned long long *stv = status;
-                long long base = 0;
-                if (g == 0) {
-                    stv[0] = K3F_PFX | total;
-                } else {
+            // decoupled look-back, one warp wide: 32 predecessors per step (lane l looks at grid q - l)
+            const unsigned long long total = (unsigned long long)run;
+            volatile unsigned long long *stv = status;
+            long long base = 0;
+            if (g == 0) {
+                if (lane == 0) stv[0] = K3F_PFX | total;
+            } else {
+                if (lane == 0) {
                     stv[g] = K3F_AGG | total;
                     __threadfence();
-                    int q = g - 1;
-                    for (;;) {
-                        const unsigned long long sv = stv[q];
-                        if (sv == 0ull) { __nanosleep(40); continue; }
-                        base += (long long)(sv & K3F_VAL);
-                        if (sv & K3F_PFX) break;
-                        --q;
-                    }
-                    stv[g] = K3F_PFX | ((unsigned long long)base + total);
                 }
+                int q = g - 1;
+                for (;;) {
+                    const int idx = q - lane;
+                    unsigned long long sv = 2ull << 62;                                   // before grid 0: prefix 0
+                    if (idx >= 0) sv = stv[idx];
+                    const unsigned not_ready = __ballot_sync(0xffffffffu, sv == 0ull);
+                    const unsigned is_pfx = __ballot_sync(0xffffffffu, (sv & K3F_PFX) != 0ull);
+                    const int first_pfx = is_pfx ? __ffs(is_pfx) - 1 : 32;
+                    const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+                    if (first_nr < first_pfx) {              // a predecessor on the way has not published yet
+                        __nanosleep(40);
+                        continue;
+                    }
+                    long long v = (lane <= first_pfx) ? (long long)(sv & K3F_VAL) : 0ll;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    base += v;
+                    if (first_pfx < 32) break;
+                    q -= 32;
+                }
+                if (lane == 0) stv[g] = K3F_PFX | ((unsigned long long)base + total);
+            }
+            if (lane == 0) {
                 item_offsets[g] = base;
                 if (g == n_grids - 1) item_offsets[n_grids] = base + (long long)total;
                 s_base = base;
