@@ -186,3 +186,27 @@ def test_default_grid_specialisation_is_bit_identical(hm, golden_scans):
         noise = rng.uniform(-1, 1, (len(pts), 2)).astype(np.float32)
         for ml in (20.0, 80.0):
             assert hm.hm_defgrid_mismatches(ml, pts.ctypes.data_as(fp), len(pts), 4, noise.ctypes.data_as(fp)) == 0
+
+
+def test_random_bit_patterns(hm, orc):
+    """x, y, z drawn uniformly from ALL float32 bit patterns (every exponent, denormals, infinities, NaNs, both
+    zeros): the exact path equals the oracle point for point, and the screened path never accepts a wrong bin."""
+    rng = np.random.default_rng(2026)
+    n = 300000
+    bits = rng.integers(0, 2 ** 32, (n, 4), dtype=np.uint64).astype(np.uint32)
+    pts = bits.view(np.float32)
+    # half of the points get moderate magnitudes in x/y so that the in-range code paths are fuzzed too
+    m = rng.random(n) < 0.5
+    pts[m, 0] = (rng.standard_normal(m.sum()) * 15).astype(np.float32)
+    pts[m, 1] = (rng.standard_normal(m.sum()) * 15).astype(np.float32)
+    for var in (0, 1):
+        for full in (1, 0):
+            cell, st, z = bin_exact(hm, pts, 160, 720, 20.0, var, full)
+            with np.errstate(all="ignore"):
+                o, stt = orc.sc_build(pts, orc.Params(160, 720, 20.0, var, bool(full)))
+            g = grid_from(cell, st, z, 160, 720, full)
+            assert ((g != o) & ~(np.isnan(g) & np.isnan(o))).sum() == 0
+            assert (st == 2).sum() == stt["n_nonfinite"] and (st == 3).sum() == stt["n_sector_overflow"]
+            assert (st == 4).sum() == stt["n_out_of_range"] and (st == 1).sum() == stt["n_clamped_ring"]
+            bad, _ = _check_fast(hm, pts, var=var, full=full, noise_mode="rand")
+            assert bad == 0
