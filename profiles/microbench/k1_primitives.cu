@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include "../../distropointclouds_b200/csrc/dsc_math.cuh"
 namespace cg = cooperative_groups;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
@@ -144,6 +145,154 @@ static float time_ms(F launch, int reps = 5)
     return best;
 }
 
+
+// ---- T5: does the ORDER in which 148 persistent CTAs walk the point stream matter to HBM? ---------------
+// Same loads per thread as k1_scan (768 threads, 3 x 128-bit per set, two sets), no compute.
+//   mode 0: every CTA owns whole "scans" (region_bytes each, handed out by an atomic cursor) -- 148 private fronts
+//   mode 1: CTAs take consecutive 36 KB tiles of one shared front (atomic cursor per tile)
+template <int MODE>
+__global__ void __launch_bounds__(768, 1) t5_fronts(const float4 *__restrict__ p, size_t n_vec, size_t region_vec,
+                                                    unsigned int *cursor, float *sink)
+{
+    constexpr int NT = 768, U = 3, STEP = NT * U;
+    __shared__ unsigned s_item;
+    float acc = 0.f;
+    const size_t n_items = MODE == 0 ? n_vec / region_vec : n_vec / (2 * STEP);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const size_t item = s_item;
+        if (item >= n_items) break;
+        const float4 *q = p + (MODE == 0 ? item * region_vec : item * (size_t)(2 * STEP)) + threadIdx.x;
+        const int steps = MODE == 0 ? (int)(region_vec / STEP) : 2;
+        for (int s = 0; s + 1 < steps + 1 && s < steps; s += 2) {
+            float4 a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "l"(q + (size_t)s * STEP + u * NT));
+            if (s + 1 < steps) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[u].x), "=f"(b[u].y), "=f"(b[u].z), "=f"(b[u].w) : "l"(q + (size_t)(s + 1) * STEP + u * NT));
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc += b[u].y;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += a[u].x;
+        }
+    }
+    if (acc == 1234.5f) *sink = acc;
+}
+
+// ---- T6: what does each stage of the per-point work cost at k1_scan's launch shape? -----------------------
+// Same loads as T5 mode 0 over plausible points (x, y uniform in +-25 m), then
+//   mode 0: the screened binning only (cell index folded into a dummy accumulator)
+//   mode 1: + LDS pre-check on a 62-row shared-memory key grid (cells outside it are skipped)
+//   mode 2: + ATOMS.MAX when the key is larger (the resident-row path of k1_scan, no L2 rows, no decode)
+__global__ void t6_fill(float4 *p, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t h = hash32((uint32_t)i * 2654435761u + 17u), g = hash32(h ^ 0x1234567u), k = hash32(g + 99u);
+        p[i] = make_float4((h * (1.0f / 4294967296.0f) - 0.5f) * 50.0f, (g * (1.0f / 4294967296.0f) - 0.5f) * 50.0f,
+                           (k * (1.0f / 4294967296.0f)) * 3.0f - 2.0f, 0.5f);
+    }
+}
+
+//   mode 3: + RED.MAX into a private L2 slot for the cells outside the resident rows
+//   mode 4: + the warp vote per point that k1_scan uses to park failed-screen points (none are processed here)
+//   mode 5: + per-scan decode: resident rows and L2 slot -> output grid (1.89 GB more HBM writes), re-zero, barriers
+template <int MODE>
+__global__ void __launch_bounds__(768, 1) t6_stages(const float4 *__restrict__ p, size_t n_vec, size_t region_vec,
+                                                    unsigned int *cursor, float *sink, const dsc::BinCfg cfg,
+                                                    uint32_t *__restrict__ slots, float *__restrict__ out)
+{
+    constexpr int NT = 768, U = 3, STEP = NT * U, NS = 62, S = 720;
+    extern __shared__ uint32_t rows[];
+    __shared__ unsigned s_item;
+    for (int i = threadIdx.x; i < NS * S; i += NT) rows[i] = 0;
+    float acc = 0.f;
+    unsigned qcount = 0;
+    uint32_t *slot = slots + (size_t)blockIdx.x * (size_t)((160 - NS) * S);
+    const size_t n_items = n_vec / region_vec;
+    auto point = [&](const float4 v) {
+        int ring, sector; bool beyond;
+        const bool ok = dsc::screened_core_t<true>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
+        const int cell = ring * S + sector;
+        if (MODE == 0) { acc += ok ? (float)cell : 0.f; return; }
+        const uint32_t u = __float_as_uint(v.z);
+        const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+        if (ok && cell < NS * S) {
+            const uint32_t old = rows[cell];
+            if (MODE == 1) acc += (float)(old & 1u);
+            if (MODE >= 2) { if (key > old) atomicMax(rows + cell, key); }
+        } else if (MODE >= 3 && ok) {
+            asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(slot + (cell - NS * S)), "r"(key) : "memory");
+        }
+        if (MODE >= 4) {
+            const unsigned m = __ballot_sync(0xffffffffu, !ok);
+            if (m) qcount += __popc(m);
+        }
+    };
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const size_t item = s_item;
+        if (item >= n_items) break;
+        const float4 *q = p + item * region_vec + threadIdx.x;
+        const int steps = (int)(region_vec / STEP);
+        float4 a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "l"(q + u * NT));
+        int s = 0;
+        while (s + 1 < steps) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[u].x), "=f"(b[u].y), "=f"(b[u].z), "=f"(b[u].w) : "l"(q + (size_t)(s + 1) * STEP + u * NT));
+#pragma unroll
+            for (int u = 0; u < U; ++u) point(a[u]);
+            s += 2;
+            if (s < steps) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "l"(q + (size_t)s * STEP + u * NT));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) point(b[u]);
+        }
+        if (s < steps) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) point(a[u]);
+        }
+        if (MODE >= 5) {
+            __threadfence();
+            __syncthreads();
+            float4 *oq = reinterpret_cast<float4 *>(out + item * (size_t)(160 * S));
+            for (int i = threadIdx.x; i < NS * S / 4; i += NT) {
+                const uint4 k4 = reinterpret_cast<uint4 *>(rows)[i];
+                reinterpret_cast<uint4 *>(rows)[i] = make_uint4(0, 0, 0, 0);
+                __stcs(oq + i, make_float4(dsc::key_to_float(k4.x), dsc::key_to_float(k4.y), dsc::key_to_float(k4.z), dsc::key_to_float(k4.w)));
+            }
+            const int nv = (160 - NS) * S / 4;
+            uint4 *kq = reinterpret_cast<uint4 *>(slot);
+            for (int i0 = threadIdx.x; i0 < nv; i0 += NT * 4) {
+                uint4 k4[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) if (i0 + d * NT < nv) k4[d] = __ldcg(kq + i0 + d * NT);
+#pragma unroll
+                for (int d = 0; d < 4; ++d) if (i0 + d * NT < nv) {
+                    __stcs(oq + NS * S / 4 + i0 + d * NT, make_float4(dsc::key_to_float(k4[d].x), dsc::key_to_float(k4[d].y), dsc::key_to_float(k4[d].z), dsc::key_to_float(k4[d].w)));
+                    __stcg(kq + i0 + d * NT, make_uint4(0, 0, 0, 0));
+                }
+            }
+            __threadfence();
+        }
+    }
+    if (acc == 1234.5f || qcount == 0xffffffffu) *sink = acc;
+}
+
 int main()
 {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
@@ -212,6 +361,73 @@ int main()
         printf("T4 global red.max scattered                              : %.1f Gop/s chip\n", ops / m1 / 1e6);
         printf("T4 global ld.cg precheck + red.max                       : %.1f Gop/s chip\n", ops / m2 / 1e6);
         CK(cudaFree(grids));
+    }
+    // T5
+    {
+        const size_t region_vec = 120000;                       // one 120 000-point scan = 1.92 MB
+        const size_t n_vec = region_vec * 4096;                 // 7.86 GB
+        float4 *buf; unsigned int *cur; float *sink5;
+        CK(cudaMalloc(&buf, n_vec * 16)); CK(cudaMalloc(&cur, 4)); CK(cudaMalloc(&sink5, 4));
+        CK(cudaMemset(buf, 0, n_vec * 16));
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int mode = 0; mode < 2; ++mode) {
+            float best = 1e9f;
+            for (int rep = 0; rep < 5; ++rep) {
+                CK(cudaMemset(cur, 0, 4));
+                CK(cudaEventRecord(e0));
+                if (mode == 0) t5_fronts<0><<<148, 768>>>(buf, n_vec, region_vec, cur, sink5);
+                else t5_fronts<1><<<148, 768>>>(buf, n_vec, region_vec, cur, sink5);
+                CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (ms < best) best = ms;
+            }
+            printf("T5 148 CTAs x 768 thr, 2 x 3 LDG.128 per thread, %s: %.1f GB/s (%.3f ms for 7.86 GB)\n",
+                   mode == 0 ? "148 private fronts (one 1.92 MB scan per CTA at a time)" : "one shared front (36 KB tiles in order)     ",
+                   n_vec * 16.0 / best / 1e6, best);
+        }
+        CK(cudaFree(buf)); CK(cudaFree(cur)); CK(cudaFree(sink5));
+    }
+    // T6
+    {
+        const size_t region_vec = 120000 / 2304 * 2304;         // whole steps only
+        const size_t n_vec = region_vec * 4096;
+        float4 *buf; unsigned int *cur; float *sink6;
+        CK(cudaMalloc(&buf, n_vec * 16)); CK(cudaMalloc(&cur, 4)); CK(cudaMalloc(&sink6, 4));
+        t6_fill<<<148 * 8, 256>>>(buf, n_vec);
+        CK(cudaDeviceSynchronize());
+        const dsc::BinCfg cfg = dsc::make_bin_cfg(160, 720, 20.0, 0, 1, 2.0f, 0, 0);
+        const int smem = 62 * 720 * 4;
+        CK(cudaFuncSetAttribute(t6_stages<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(t6_stages<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(t6_stages<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        uint32_t *slots; float *outg;
+        CK(cudaMalloc(&slots, (size_t)148 * 98 * 720 * 4)); CK(cudaMemset(slots, 0, (size_t)148 * 98 * 720 * 4));
+        CK(cudaMalloc(&outg, (size_t)4096 * 160 * 720 * 4));
+        CK(cudaFuncSetAttribute(t6_stages<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(t6_stages<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(t6_stages<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const char *names[6] = {"loads + screened binning", "+ LDS pre-check (62 resident rows)", "+ ATOMS.MAX when larger",
+                                "+ RED.MAX to a private L2 slot", "+ warp vote per point", "+ per-scan decode and grid write-out"};
+        for (int mode = 0; mode < 6; ++mode) {
+            float best = 1e9f;
+            for (int rep = 0; rep < 5; ++rep) {
+                CK(cudaMemset(cur, 0, 4));
+                CK(cudaEventRecord(e0));
+                if (mode == 0) t6_stages<0><<<148, 768, smem>>>(buf, n_vec, region_vec, cur, sink6, cfg, slots, outg);
+                else if (mode == 1) t6_stages<1><<<148, 768, smem>>>(buf, n_vec, region_vec, cur, sink6, cfg, slots, outg);
+                else if (mode == 2) t6_stages<2><<<148, 768, smem>>>(buf, n_vec, region_vec, cur, sink6, cfg, slots, outg);
+                else if (mode == 3) t6_stages<3><<<148, 768, smem>>>(buf, n_vec, region_vec, cur, sink6, cfg, slots, outg);
+                else if (mode == 4) t6_stages<4><<<148, 768, smem>>>(buf, n_vec, region_vec, cur, sink6, cfg, slots, outg);
+                else t6_stages<5><<<148, 768, smem>>>(buf, n_vec, region_vec, cur, sink6, cfg, slots, outg);
+                CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (ms < best) best = ms;
+            }
+            printf("T6 %-36s: %.3f ms for %.2f GB = %.1f GB/s, %.1f Gpts/s\n", names[mode], best, n_vec * 16.0 / 1e9,
+                   n_vec * 16.0 / best / 1e6, n_vec / best / 1e6);
+        }
+        CK(cudaFree(buf)); CK(cudaFree(cur)); CK(cudaFree(sink6));
     }
     return 0;
 }
