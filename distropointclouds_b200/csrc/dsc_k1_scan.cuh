@@ -9,9 +9,6 @@
 // rows and slot to floats (coalesced 128-bit streaming stores) and re-zeroes both.  There is no synchronisation
 // between CTAs for whole-scan items; HBM sees each point once and each output cell once.
 constexpr int SC_THREADS = 1024;
-#ifndef SC_RED_MERGE
-#define SC_RED_MERGE 1                // 1: one RED.MAX per distinct cell per warp (match.any + redux.max)
-#endif
 #ifndef SC_TOUCH
 #define SC_TOUCH 0                    // 1: touched-segment flags for the L2-row decode (measured: slower, see r1_notes.md)
 #endif
@@ -86,18 +83,7 @@ __device__ __forceinline__ void sc_update(const float zv, const int cell, uint32
         if (key > lds_u32(addr)) reds_max_u32(addr, key);   // most points are not a new maximum
         return;
     }
-#if SC_RED_MERGE
-    {   // points of one beam that are neighbours in the file fall into the same far cell in runs: one RED per
-        // distinct cell per warp (the L2 reductions are the most expensive thing a point can do: r1_notes.md)
-        const unsigned peers = __match_any_sync(__activemask(), cell);
-        const uint32_t kmax = __reduce_max_sync(peers, key);
-        unsigned lane;
-        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
-        if ((peers & ((1u << lane) - 1u)) == 0u) red_max_global(grid + cell, kmax);
-    }
-#else
     red_max_global(grid + cell, key);
-#endif
     if constexpr (TOUCH) sts_u8(sm.base - flag_bytes + (uint32_t)(cell >> SC_SEG_SHIFT), 1u);
 }
 
