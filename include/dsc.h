@@ -88,9 +88,16 @@ const char *dsc_last_error(const dsc_ctx *ctx);
  * (dsc_set_timing(ctx,1)); the call then synchronises the stream.  -1 if not available. */
 int dsc_set_timing(dsc_ctx *ctx, int enabled);
 float dsc_last_kernel_ms(const dsc_ctx *ctx);
-/* Engine options (debugging / A-B measurements):
- *   "k1_impl"  0 = auto, 1 = chunked L2-key kernels, 2 = shared-memory half-grid kernel,
- *              3 = scan-per-CTA kernel, 4 = tile kernel;  plus kernel-shape knobs (see dsc_api.cu) */
+/* Engine options (debugging / A-B measurements; defaults are the measured best, see profiles/r1_notes.md):
+ *   "k1_impl"        0 = auto (k1_scan; generic fallback for 12-byte stride / odd shapes), 1 = chunked L2-key
+ *                    kernels, 2 = CTA-pair half-grid kernel, 3 = k1_scan only, 4 = tile-scheduler kernel
+ *   "sc_cfg"         k1_scan launch shape: 0 = 768 threads x 3 loads, 1 = 1024 x 3, 2 = 1024 x 2
+ *   "sc_smem_rows"   resident ring rows of k1_scan (-1 = as many as the carve-out allows)
+ *   "sc_split"       -1 = auto, 0 = never cut scans into work items, 1 = always
+ *   "sc_item_points" target points per work item when scans are cut (default 131072)
+ *   "sc_loader"      0 = 128-bit register loads, 1 = TMA ring (cp.async.bulk + mbarrier)
+ *   "l2_persist"     1 = keep the private key slots in the persisting part of L2 during the launch
+ *   "st_cfg", "st_slots", "hg_cfg", "pf_dist", "no_defgrid"   knobs of the A/B kernels */
 int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value);
 /* Number of engine kernels launched since the context was created. */
 int64_t dsc_kernel_launches(const dsc_ctx *ctx);
