@@ -206,13 +206,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     eng = Engine(local_rank)
-    for name in ("k1_impl", "hg_cfg", "st_cfg", "sc_cfg", "no_defgrid", "sc_smem_rows", "sc_split", "sc_item_points", "sc_loader", "l2_persist"):
+    for name in ("k1_impl", "sc_cfg", "no_defgrid", "sc_smem_rows", "sc_split", "sc_item_points"):
         v = getattr(args, name)
         if v is not None:
-            eng.set_option(name, v)
-    for name in ("pf_dist", "st_slots"):
-        v = getattr(args, name)
-        if v is not None and v >= 0 and not (name == "st_slots" and v == 0):
             eng.set_option(name, v)
     params = ScanContextParams(R, S, MAXLEN)
     B, Pn, beams, n_base, desc = workload_cfg(args)
@@ -348,7 +344,7 @@ def run_ours(args):
         line = base_line(args, world, desc, Pn)
         line["config"]["l2_policy"] = (f"inputs larger than L2: {B * Pn * 16 / 2**20:.0f} MiB of points per step vs "
                                        f"{l2_mb:.0f} MiB L2" if flush is None else "256 MiB flush buffer written between steps")
-        line["config"]["k1_impl"] = {None: "auto", 0: "auto", 1: "l2keys", 2: "halfgrid", 3: "scan", 4: "tile"}[args.k1_impl]
+        line["config"]["k1_impl"] = {None: "auto", 0: "auto", 1: "l2keys", 3: "scan"}[args.k1_impl]
         if wl == "cnn":
             line["config"]["cnn_precision"] = args.cnn_precision
         line.update({
@@ -401,8 +397,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     # A/B knobs of the engine (see dsc_api.cu); None = engine default
-    for name in ("k1-impl", "hg-cfg", "st-cfg", "sc-cfg", "no-defgrid", "sc-smem-rows", "sc-split", "sc-item-points", "sc-loader", "l2-persist",
-                 "pf-dist", "st-slots"):
+    for name in ("k1-impl", "sc-cfg", "no-defgrid", "sc-smem-rows", "sc-split", "sc-item-points"):
         ap.add_argument("--" + name, type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":

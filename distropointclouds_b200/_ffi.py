@@ -18,7 +18,8 @@ FLAG_GAP_F32, FLAG_EXACT_ONLY = 1, 2
 
 EXPORTS = (
     "dsc_version", "dsc_create", "dsc_destroy", "dsc_last_error", "dsc_set_timing", "dsc_last_kernel_ms",
-    "dsc_kernel_launches", "dsc_set_option", "dsc_host_alloc", "dsc_host_free", "dsc_sc_build_batch", "dsc_sc_normalize01",
+    "dsc_kernel_launches", "dsc_set_option", "dsc_host_alloc", "dsc_host_free", "dsc_sc_build_batch",
+    "dsc_sc_build_batch_f64", "dsc_sc_normalize01",
     "dsc_set_polar_tables", "dsc_raster_boxes", "dsc_reconstruct_batch", "dsc_covered_mask",
     "dsc_gather_cells",
 )
@@ -44,6 +45,7 @@ class DscScanStats(C.Structure):
         ("n_clamped_ring", C.c_int64),
         ("n_out_of_range", C.c_int64),
         ("n_slow_path", C.c_int64),
+        ("n_boundary", C.c_int64),
     ]
 
 
@@ -83,6 +85,7 @@ def load() -> C.CDLL:
     L.dsc_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.dsc_host_free.argtypes = [vp, vp]
     L.dsc_sc_build_batch.argtypes = [vp, C.POINTER(DscParams), vp, vp, ip, ip, ip, vp, vp, vp, vp]
+    L.dsc_sc_build_batch_f64.argtypes = [vp, C.POINTER(DscParams), C.c_double, vp, vp, ip, ip, ip, vp, vp, vp]
     L.dsc_sc_normalize01.argtypes = [vp, vp, ip, C.c_int64, ip, vp, vp]
     L.dsc_set_polar_tables.argtypes = [vp, ip, ip, vp, vp, vp]
     L.dsc_raster_boxes.argtypes = [vp, vp, ip, ip, vp, vp, C.c_int64, vp, vp]

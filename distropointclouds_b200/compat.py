@@ -26,14 +26,6 @@ device = 0          # GPU the patched methods run on
 strict = True       # raise IndexError where variant A of the reference would
 
 
-def _f32_points(pts, who):
-    pts = np.asarray(pts)
-    if pts.dtype != np.float32:
-        raise TypeError(f"{who}: the engine bins float32 points (the .bin dtype); got {pts.dtype} "
-                        "(float64 clouds only come from the Open3D down-sampler, which is out of scope)")
-    return pts
-
-
 # ---- replacements -----------------------------------------------------------------------------
 
 def _ptcloud2sc_vectorized(self, ptcloud, num_sector, num_ring, max_length):
@@ -43,11 +35,11 @@ def _ptcloud2sc_vectorized(self, ptcloud, num_sector, num_ring, max_length):
         num_ring=int(num_ring), num_sector=int(num_sector), max_length=float(max_length), variant=_ffi.VARIANT_A,
         full_height=bool(cls.use_full_height_range), height_offset=float(cls.custom_height_offset),
         gap_f32=not (_is_np_int(num_ring) or _is_np_int(num_sector) or isinstance(max_length, np.floating)))
-    grids, _, stats = default_engine(device).build_scans([_f32_points(ptcloud, "ptcloud2sc_vectorized")], params)
-    cls.last_stats = dict(zip(_STATS, (int(v) for v in stats[0])))
+    grid, stats = default_engine(device).build_any(ptcloud, params)       # float32 (.bin) or float64 (down-sampled)
+    cls.last_stats = dict(zip(_STATS, (int(v) for v in stats)))
     if strict:
-        _raise_like_reference(stats[0])
-    return grids[0].astype(np.float64)
+        _raise_like_reference(stats)
+    return grid
 
 
 def _sc_to_pointcloud_loop(self, sc_data):
@@ -80,9 +72,10 @@ def _scan_context_b(self, pts_xyz):
         return np.zeros((self.ring_res, self.sector_res), dtype=np.float32)
     params = ScanContextParams(int(self.ring_res), int(self.sector_res), float(self.max_length), _ffi.VARIANT_B,
                                bool(self.use_full_height_range), float(self.custom_height_offset))
-    grids, _, stats = default_engine(device).build_scans([_f32_points(pts, "_scan_context")], params)
-    self.last_stats = dict(zip(_STATS, (int(v) for v in stats[0])))
-    return grids[0]
+    # the live node hands over float64 (Open3D-downsampled, scan_context_node.py:100,161); ROS float32 also works
+    grid, stats = default_engine(device).build_any(pts, params)
+    self.last_stats = dict(zip(_STATS, (int(v) for v in stats)))
+    return grid
 
 
 def _rec_sc_to_pointcloud(self, sc_data):

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 void dsc_k1_release(dsc_ctx *ctx);
+void dsc_k1f64_release(dsc_ctx *ctx);
 
 extern "C" const char *dsc_version(void) { return DSC_VERSION_STRING; }
 
@@ -24,12 +25,8 @@ extern "C" int dsc_create(int device, dsc_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = prop.l2CacheSize;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    ctx->persist_max = (size_t)prop.persistingL2CacheMaxSize;
-    ctx->window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (const char *e = getenv("DSC_K1_IMPL")) ctx->k1_impl = atoi(e);   // debugging / A-B benchmarking only
-    if (const char *e = getenv("DSC_SC_LOADER")) ctx->sc_loader = atoi(e);
-    if (const char *e = getenv("DSC_SC_CFG")) ctx->sc_cfg = atoi(e);
     bool ok = cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_call, cudaEventDisableTiming) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_k, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
@@ -48,6 +45,7 @@ extern "C" int dsc_destroy(dsc_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     dsc_k1_release(ctx);
+    dsc_k1f64_release(ctx);
     if (ctx->d_rc) cudaFree(ctx->d_rc);
     if (ctx->d_cos) cudaFree(ctx->d_cos);
     if (ctx->d_sin) cudaFree(ctx->d_sin);
@@ -55,6 +53,7 @@ extern "C" int dsc_destroy(dsc_ctx *ctx)
     if (ctx->work_counter) cudaFree(ctx->work_counter);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_call) cudaEventDestroy(ctx->ev_call);
     for (int i = 0; i < DSC_NBUF; ++i) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
@@ -77,18 +76,12 @@ extern "C" int dsc_set_timing(dsc_ctx *ctx, int enabled)
 extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return DSC_ERR_INVALID;
-    if (!strcmp(name, "k1_impl") && value >= 0 && value <= 4) { ctx->k1_impl = (int)value; return DSC_OK; }
+    if (!strcmp(name, "k1_impl") && (value == 0 || value == 1 || value == 3)) { ctx->k1_impl = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_smem_rows") && value >= -1 && value <= 65536) { ctx->sc_smem_rows = (int)value; return DSC_OK; }
     if (!strcmp(name, "no_defgrid") && value >= 0 && value <= 1) { ctx->no_defgrid = (int)value; return DSC_OK; }
-    if (!strcmp(name, "l2_persist") && value >= 0 && value <= 1) { ctx->l2_persist = (int)value; return DSC_OK; }
-    if (!strcmp(name, "sc_loader") && value >= 0 && value <= 1) { ctx->sc_loader = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_split") && value >= -1 && value <= 1) { ctx->sc_split = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_item_points") && value >= 1024 && value <= (1 << 30)) { ctx->sc_item_points = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_cfg") && value >= 0 && value <= 2) { ctx->sc_cfg = (int)value; return DSC_OK; }
-    if (!strcmp(name, "st_cfg") && value >= 0 && value <= 1) { ctx->st_cfg = (int)value; return DSC_OK; }
-    if (!strcmp(name, "st_slots") && value >= 1 && value <= 4096) { ctx->st_slots = (int)value; return DSC_OK; }
-    if (!strcmp(name, "pf_dist") && value >= 0 && value <= 64) { ctx->pf_dist = (int)value; return DSC_OK; }
-    if (!strcmp(name, "hg_cfg") && value >= 0 && value <= 2) { ctx->hg_cfg = (int)value; return DSC_OK; }
     DSC_FAIL(ctx, DSC_ERR_INVALID, std::string("unknown option or bad value: ") + name);
 }
 extern "C" float dsc_last_kernel_ms(const dsc_ctx *ctx) { return ctx ? ctx->last_ms : -1.0f; }
@@ -106,6 +99,18 @@ extern "C" int dsc_host_free(dsc_ctx *ctx, void *p)
 {
     if (!ctx) return DSC_ERR_INVALID;
     if (p) DSC_CUDA(ctx, cudaFreeHost(p));
+    return DSC_OK;
+}
+
+int dsc_enter_stream(dsc_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->ev_call_set) DSC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_call, 0));
+    return DSC_OK;
+}
+int dsc_leave_stream(dsc_ctx *ctx, cudaStream_t st)
+{
+    DSC_CUDA(ctx, cudaEventRecord(ctx->ev_call, st));
+    ctx->ev_call_set = 1;
     return DSC_OK;
 }
 

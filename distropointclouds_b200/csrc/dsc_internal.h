@@ -13,6 +13,8 @@
 #ifndef DSC_NBUF
 #define DSC_NBUF 3
 #endif
+#define DSC_OFF_RING 4
+#define DSC_STATS_WORDS ((int)(sizeof(dsc_scan_stats) / 8))     // counters per scan, as 64-bit words
 
 struct dsc_ctx {
     int device = 0;
@@ -25,28 +27,31 @@ struct dsc_ctx {
     int sc_smem_rows = -1;           // scan kernel: ring rows kept in shared memory (-1 = as many as fit, 0 = none)
     int no_defgrid = 0;              // 1: do not use the default-grid specialisation (A/B runs)
     int sc_cfg = 0;                  // scan kernel launch shape (screened default-grid kernels): 0 = 768 thr x 3 loads, 1 = 1024x3, 2 = 1024x2
-    size_t persist_max = 0, window_max = 0, persist_set = 0;   // L2 persistence limits of the device
-    int l2_persist = 0;              // 1: keep the key slots in the persisting part of L2 during the launch
-    int sc_loader = 0;               // scan kernel point loader: 0 = 128-bit register loads, 1-4 = TMA ring shapes (k1_ring)
     int sc_split = -1;               // scan kernel: -1 auto, 0 never split scans into items, 1 always
     int sc_item_points = 131072;     // scan kernel: target points per work item when scans are split
-    int st_cfg = 0;                  // streaming kernel shape: 0 = 8 pts/thread, 3 CTAs/SM; 1 = 6 pts/thread, 4 CTAs/SM
-    int st_slots = 64;               // key-grid slots of the streaming kernel (L2-resident ring)
-    void *sync_buf = nullptr;        // streaming kernel: cursor, per-scan counters, tile table
+    void *sync_buf = nullptr;        // scan kernel: work-item cursor, per-scan retire counters, item table
     size_t sync_cap = 0;
-    int pf_dist = 0;                 // bulk L2 prefetch distance in steps (0 = off)
-    int hg_cfg = 0;                  // half-grid launch shape: 0 = 1024 thr x 2 loads x 2 sets, 1 = 1024x3x2, 2 = 512x4x2 (A/B runs)
-    int k1_impl = 0;                 // 0 auto, 1 chunked L2-key kernels, 2 half-grid, 3 scan-per-CTA, 4 tile kernel
+    int k1_impl = 0;                 // 0 auto, 1 generic L2-key kernels only, 3 scan kernel whenever the shape allows
     float last_ms = -1.0f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // K1 scratch
-    uint32_t *keys = nullptr;        // [keys_slots][cells] order-preserving keys (zero == empty)
+    uint32_t *keys = nullptr;        // generic path: [slots][cells] order-preserving keys (zero == empty; left zeroed)
     size_t keys_bytes = 0;
-    int64_t *d_offsets = nullptr;    // device copy of the caller's offsets
-    size_t d_offsets_cap = 0;        // in elements
-    int64_t *h_offsets = nullptr;    // pinned staging for offsets
-    size_t h_offsets_cap = 0;
+    void *spill = nullptr;           // scan kernel: per-CTA spill lists of (cell, key) pairs
+    size_t spill_bytes = 0;
+    void *keys64 = nullptr;          // float64-input path: [slots][cells] 64-bit (variant A) or 32-bit (variant B) keys
+    size_t keys64_bytes = 0;
+    struct OffSlot {                 // offsets of a device-mode call: pinned staging + device copy + "consumed" event
+        int64_t *h = nullptr, *d = nullptr;
+        size_t cap = 0;              // in elements
+        cudaEvent_t ev = nullptr;
+        int used = 0;
+    };
+    OffSlot off[DSC_OFF_RING];
+    int off_next = 0;
+    cudaEvent_t ev_call = nullptr;   // end of the last device-mode call (the engine scratch is shared between calls)
+    int ev_call_set = 0;
     uint32_t *minmax = nullptr;      // [n][2] key-encoded per-grid min / max for normalise
     size_t minmax_cap = 0;           // in grids
     int *work_counter = nullptr;     // persistent-kernel tile cursor
@@ -92,3 +97,10 @@ struct dsc_ctx {
 int dsc_reserve_scratch(dsc_ctx *ctx, size_t bytes);
 // checks the launch that was just issued
 int dsc_check_launch(dsc_ctx *ctx, const char *what);
+// Device-mode calls are asynchronous and share the context's scratch buffers: dsc_enter_stream orders the call
+// after the previous one (a no-op wait when both use the same stream), dsc_leave_stream marks its end.
+int dsc_enter_stream(dsc_ctx *ctx, cudaStream_t st);
+int dsc_leave_stream(dsc_ctx *ctx, cudaStream_t st);
+// Offsets of a device-mode call -> ctx->off[*slot_out].d (a ring of pinned + device buffers guarded by events; the
+// caller records ctx->off[slot].ev after the kernels that read them and sets .used)
+int dsc_upload_offsets(dsc_ctx *ctx, const int64_t *offsets, int n_scans, cudaStream_t st, int *slot_out);

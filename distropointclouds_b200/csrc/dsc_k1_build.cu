@@ -20,7 +20,7 @@ using dsc::BinResult;
 
 #include "dsc_k1_common.cuh"
 #include "dsc_k1_scan.cuh"
-#include "dsc_k1_variants.cuh"
+#include "dsc_k1_fallback.cuh"
 #include "dsc_k4.cuh"
 
 }  // namespace
@@ -140,14 +140,34 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         const int64_t n = h_offsets[s + 1] - h_offsets[s];
         split_items += n > item_pts ? (n + item_pts - 1) / item_pts : 1;
     }
-    const bool sc_shape_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0;
+    const bool sc_shape_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1;
     const bool want_split = ctx->sc_split == 1 ||
                             (ctx->sc_split < 0 && (n_scans < 2 * ctx->sm_count || max_pts > 3 * ctx->sc_item_points) &&
                              split_items > n_scans);
-    const bool split = sc_shape_ok && want_split && (ctx->k1_impl == 0 || ctx->k1_impl == 3) &&
-                       split_items < 0x7fff0000LL;
-    const bool sc_ok = sc_shape_ok &&
-                       (split || (ctx->k1_impl == 0 ? n_scans >= ctx->sm_count / 2 : ctx->k1_impl == 3));
+    const bool split = sc_shape_ok && want_split && split_items < 0x7fff0000LL;
+    const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
+    // launch shape (threads x 128-bit loads per thread per register set); shapes other than 0 exist for the
+    // screened default-grid kernels only.  Fewer threads = more registers per thread (no spills), fewer warps.
+    int shape = (cfg.fast_ok && defgrid) ? ctx->sc_cfg : 2;                     // the generic kernels are 1024 x 2
+    if (shape != 1 && shape != 2) shape = 0;
+    const int nthreads = shape == 0 ? 768 : 1024;
+    const size_t row_bytes = (size_t)p->num_sector * 4;
+    const size_t q_bytes = cfg.fast_ok ? (size_t)SCQ_WARP_BYTES * (nthreads / 32) : 0;       // per-warp exact-path queues
+    // Resident rows.  Shared memory and L1 share 256 KB per SM; beyond the 196 KB carve-out step (164 KB for the
+    // 1024-thread shapes) the streaming loads starve (profiles/r1_notes.md: 60 rows 1.99 ms, 64 rows 2.14 ms).
+    // Split items have no second pass -- every non-resident point is a RED.MAX on a grid that 16 CTAs share --
+    // and want every row they can get (dense2m: 62 rows 0.62 ms, 72 rows 0.53 ms).
+    const size_t sc_budget = split ? ctx->smem_optin : (size_t)(nthreads < 1024 ? 196 : 164) * 1024 - 1024 - 256 - q_bytes;
+    const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
+    int ns = (int)((sc_budget < sc_max ? sc_budget : sc_max) / row_bytes);
+    if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                          // A/B override
+    if ((size_t)ns * row_bytes > sc_max) ns = (int)(sc_max / row_bytes);
+    if (ns > p->num_ring) ns = p->num_ring;
+    // whole scans reduce the rings beyond the resident ones in bands of ns rows, re-reading the spill list once
+    // per band: grids with very many rings for their row size go to the generic path instead
+    const int bands = ns >= 2 ? (p->num_ring - ns + ns - 1) / ns : 0x7fffffff;
+    const bool sc_ok = sc_shape_ok && ns >= 2 && (split || bands <= 8) &&
+                       (split || ctx->k1_impl == 3 || n_scans >= ctx->sm_count / 2);
     if (sc_ok) {
         int ctas = ctx->sm_count;
         const int64_t n_items = split ? split_items : (int64_t)n_scans;
@@ -155,6 +175,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         // sync block: [cursor (16 B)] [done[n_scans]] [item_base[n_scans+1] (ragged batches)]
         SplitArgs spa = {nullptr, nullptr, 0, 0};
         size_t sync_bytes = 16;
+        size_t spill_cap = 0;                    // entries per CTA
         if (split) {
             bool uniform = true;
             const int64_t n0 = h_offsets[1] - h_offsets[0];
@@ -185,99 +206,30 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             DSC_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)n_scans * cells * 4, st));
         } else {
             if ((rc = dsc_reserve_sync(ctx, 256))) return rc;
+            // spill lists: one region per CTA, big enough for every point of the largest scan (only the part that
+            // is used -- the points outside the resident rings, ~15 % on KITTI-like scans -- is ever touched)
+            spill_cap = (size_t)((max_pts + nthreads - 1) / nthreads) * (size_t)nthreads;
+            if (spill_cap < (size_t)nthreads) spill_cap = (size_t)nthreads;
+            const size_t need = (size_t)ctas * spill_cap * sizeof(uint2);
+            if (need > ctx->spill_bytes) {
+                if (ctx->spill) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->spill); }
+                ctx->spill = nullptr;
+                ctx->spill_bytes = 0;
+                DSC_CUDA(ctx, cudaMalloc(&ctx->spill, need));
+                ctx->spill_bytes = need;
+            }
         }
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
         DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, sync_bytes, st));
         unsigned long long *stp = (unsigned long long *)stats;
-        const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
         const bool full = p->full_height != 0;
-        const size_t row_bytes = (size_t)p->num_sector * 4;
-        // ---- TMA-ring loader (k1_ring): default grid + screened path only; everything else uses k1_scan ----
-        const int ring_cfg = (cfg.fast_ok && defgrid) ? ctx->sc_loader : 0;
-        if (ring_cfg > 0) {
-            // 2 points per thread x 3 stages (96 KB); 1 x 4, 1 x 6 and 1 x 3 were measured and are slower (r1_notes.md)
-            const size_t ring_bytes = 98304;
-            int ns = (int)((ctx->smem_optin - ring_bytes - 1024) / row_bytes);
-            if (ctx->sc_smem_rows >= 0 && ctx->sc_smem_rows < ns) ns = ctx->sc_smem_rows;
-            if (ns > p->num_ring) ns = p->num_ring;
-            if (ns < 2) ns = 0;
-            const size_t rg_smem = (((size_t)ns * row_bytes + 127) & ~(size_t)127) + ring_bytes;
-            if ((rc = ensure_keys(ctx, split ? 0 : (size_t)ctx->sm_count * cells * 4, st))) return rc;   // full-size slots
-#define RG_LAUNCH3(V, H, U, N, SP)                                                                              \
-    do {                                                                                                        \
-        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_ring<true, V, H, U, N, true, SP>,                                 \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rg_smem));         \
-        k1_ring<true, V, H, U, N, true, SP><<<ctas, SC_THREADS, rg_smem, st>>>(pts, d_offsets, n_scans,         \
-                                                                               ctx->keys, out, stp, cursor, ns, \
-                                                                               cfg, spa);                       \
-    } while (0)
-#define RG_LAUNCH2(V, H, U, N)                                                                                  \
-    do {                                                                                                        \
-        if (split) RG_LAUNCH3(V, H, U, N, true); else RG_LAUNCH3(V, H, U, N, false);                            \
-    } while (0)
-#define RG_LAUNCH(V, H)                                                                                         \
-    do {                                                                                                        \
-        RG_LAUNCH2(V, H, 2, 3);                                                                            \
-    } while (0)
-            if (p->variant == 0) { if (full) RG_LAUNCH(0, true); else RG_LAUNCH(0, false); }
-            else                 { if (full) RG_LAUNCH(1, true); else RG_LAUNCH(1, false); }
-#undef RG_LAUNCH
-#undef RG_LAUNCH2
-#undef RG_LAUNCH3
-            if ((rc = dsc_check_launch(ctx, "k1_ring"))) return rc;
-            if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
-            return DSC_OK;
-        }
-        // launch shape (threads x 128-bit loads per thread per register set); shapes other than 0 exist for the
-        // screened default-grid kernels only.  Fewer threads = more registers per thread (no spills), fewer warps.
-        int shape = (cfg.fast_ok && defgrid) ? ctx->sc_cfg : 2;                 // the generic kernels are 1024 x 2
-        if (shape != 1 && shape != 2) shape = 0;
-        const int nthreads = shape == 0 ? 768 : 1024;
-        const size_t q_bytes = cfg.fast_ok ? (size_t)SCQ_WARP_BYTES * (nthreads / 32) : 0;   // per-warp exact-path queues
-        // Resident rows.  Shared memory and L1 share 256 KB per SM and the 128-bit streaming loads stage through
-        // L1: beyond the 196 KB carve-out step (164 KB for the 1024-thread shapes) the loader starves
-        // (profiles/r1_notes.md: 60 rows 1.99 ms, 64 rows 2.14 ms).  Split scans have no private L2 slot --
-        // every non-resident point is a RED.MAX on a grid that 16 CTAs share -- and want every row they can get
-        // (dense2m: 62 rows 0.62 ms, 72 rows 0.53 ms).
-        const size_t sc_budget = split ? ctx->smem_optin
-                                       : (size_t)(nthreads < 1024 ? 196 : 164) * 1024 - 1024 - 256 - q_bytes;
-        const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
-        // touched-segment flags (whole-scan items of the screened kernels): one byte per 16 cells of the grid
-        const size_t f_bytes = (SC_TOUCH && cfg.fast_ok && !split) ? sc_flag_bytes((int)cells) : 0;
-        const size_t lim_bytes = (sc_budget < sc_max ? sc_budget : sc_max) - f_bytes;
-        int ns = (int)(lim_bytes / row_bytes);
-        if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                      // A/B override
-        if ((size_t)ns * row_bytes > sc_max - f_bytes) ns = (int)((sc_max - f_bytes) / row_bytes);
-        if (ns > p->num_ring) ns = p->num_ring;
-        if (ns < 2) ns = 0;
-        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes + f_bytes;
-        // private key slots (whole-scan items): the non-resident rows of one grid per CTA, L2-resident
-        const size_t slot_bytes = (size_t)(ns > 0 ? p->num_ring - ns : p->num_ring) * row_bytes;
-        const size_t need = split ? 0 : (size_t)ctx->sm_count * slot_bytes;
-        if ((rc = ensure_keys(ctx, need, st))) return rc;
-        // optional: keep the slots in the persisting part of L2 for the duration of the launch
-        cudaStreamAttrValue win;
-        memset(&win, 0, sizeof win);
-        if (ctx->l2_persist && need > 0 && ctx->persist_max > 0) {
-            const size_t want = need < ctx->persist_max ? need : ctx->persist_max;
-            if (ctx->persist_set < want) {
-                DSC_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-                ctx->persist_set = want;
-            }
-            win.accessPolicyWindow.base_ptr = ctx->keys;
-            win.accessPolicyWindow.num_bytes = need < ctx->window_max ? need : ctx->window_max;
-            const double ratio = (double)ctx->persist_set / (double)win.accessPolicyWindow.num_bytes;
-            win.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
-            win.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            win.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
-        }
+        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
 #define SC_LAUNCH4(F, V, H, U, NT, D, SP)                                                                       \
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP>,                                      \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
-        k1_scan<F, V, H, U, NT, D, SP><<<ctas, NT, sc_smem, st>>>(pts, d_offsets, n_scans, ctx->keys, out, stp, \
-                                                                  cursor, ns, cfg, spa);                        \
+        k1_scan<F, V, H, U, NT, D, SP><<<ctas, NT, sc_smem, st>>>(pts, d_offsets, n_scans, (uint2 *)ctx->spill, \
+                                                                  spill_cap, out, stp, cursor, ns, cfg, spa);   \
     } while (0)
 #define SC_LAUNCH3(F, V, H, U, NT, D)                                                                           \
     do {                                                                                                        \
@@ -303,135 +255,16 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
 #undef SC_LAUNCH3
 #undef SC_LAUNCH4
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
-        if (win.accessPolicyWindow.num_bytes) {      // leave the caller's stream as we found it
-            win.accessPolicyWindow.num_bytes = 0;
-            DSC_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &win));
-        }
         if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
         return DSC_OK;
     }
-    // ---- tile path (small batches, huge scans): persistent tile kernel, shared L2-resident slot ring ----
-    const bool st_ok = vec16 && (cells % 4) == 0 && (((uintptr_t)out) & 15) == 0 && (ctx->k1_impl == 0 || ctx->k1_impl == 4);
-    if (st_ok) {
-        int n_slots = ctx->st_slots;
-        if (n_slots > n_scans) n_slots = n_scans;
-        const size_t need = (size_t)n_slots * cells * 4;
-        if (need > ctx->keys_bytes) {
-            if (ctx->keys) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->keys); }
-            ctx->keys = nullptr;
-            ctx->keys_bytes = 0;
-            DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
-            ctx->keys_bytes = need;
-            DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
-        }
-        // tile table
-        const int ST_TILE = ST_THREADS * (ctx->st_cfg == 1 ? 6 : 8);
-        long long total_tiles = 0;
-        int uniform = -1;
-        for (int s = 0; s < n_scans; ++s) {
-            const long long t = (h_offsets[s + 1] - h_offsets[s] + ST_TILE - 1) / ST_TILE;
-            if (s == 0) uniform = (int)t; else if (t != uniform) uniform = 0;
-            total_tiles += t;
-        }
-        const size_t sync_bytes = sizeof(StreamSync) + sizeof(unsigned) * 2 * (size_t)n_scans;
-        const size_t tb_bytes = uniform > 0 ? 0 : sizeof(int64_t) * ((size_t)n_scans + 1);
-        if ((rc = dsc_reserve_sync(ctx, sync_bytes + tb_bytes + 64))) return rc;
-        StreamSync *sync = (StreamSync *)ctx->sync_buf;
-        int64_t *d_tb = nullptr;
-        if (uniform <= 0) {
-            d_tb = (int64_t *)((uint8_t *)ctx->sync_buf + ((sync_bytes + 15) & ~(size_t)15));
-            std::vector<int64_t> tb((size_t)n_scans + 1);
-            long long acc_t = 0;
-            for (int s = 0; s < n_scans; ++s) { tb[s] = acc_t; acc_t += (h_offsets[s + 1] - h_offsets[s] + ST_TILE - 1) / ST_TILE; }
-            tb[n_scans] = acc_t;
-            // pageable source: the copy is staged by the driver before the call returns
-            DSC_CUDA(ctx, cudaMemcpyAsync(d_tb, tb.data(), tb_bytes, cudaMemcpyHostToDevice, st));
-        }
-        DSC_CUDA(ctx, cudaMemsetAsync(sync, 0, sync_bytes, st));
-        if (total_tiles > 0x7fff0000LL) DSC_FAIL(ctx, DSC_ERR_INVALID, "batch too large for one call");
-        if (total_tiles > 0) {
-            unsigned long long *stp = (unsigned long long *)stats;
-            const int minb = ctx->st_cfg == 1 ? 4 : 3;
-            int grid_ctas = ctx->sm_count * minb;
-            if ((long long)grid_ctas > total_tiles) grid_ctas = (int)total_tiles;
-#define ST_LAUNCH2(F, V, H, PPT, MINB)                                                                          \
-    k1_stream<F, V, H, PPT, MINB><<<grid_ctas, ST_THREADS, 0, st>>>(pts, d_offsets, d_tb, n_scans,              \
-                                                                    (int)total_tiles, uniform, ctx->keys,       \
-                                                                    n_slots, out, stp, sync, cfg)
-#define ST_LAUNCH(F, V, H)                                                                                      \
-    do {                                                                                                        \
-        if (ctx->st_cfg == 1) ST_LAUNCH2(F, V, H, 6, 4); else ST_LAUNCH2(F, V, H, 8, 3);                        \
-    } while (0)
-            const bool full = p->full_height != 0;
-            if (cfg.fast_ok) {
-                if (p->variant == 0) { if (full) ST_LAUNCH(true, 0, true); else ST_LAUNCH(true, 0, false); }
-                else                 { if (full) ST_LAUNCH(true, 1, true); else ST_LAUNCH(true, 1, false); }
-            } else {
-                if (p->variant == 0) { if (full) ST_LAUNCH(false, 0, true); else ST_LAUNCH(false, 0, false); }
-                else                 { if (full) ST_LAUNCH(false, 1, true); else ST_LAUNCH(false, 1, false); }
-            }
-#undef ST_LAUNCH
-#undef ST_LAUNCH2
-            if ((rc = dsc_check_launch(ctx, "k1_stream"))) return rc;
-        }
-        // scans without points never retire a tile: their grids are all zeros
-        for (int s = 0; s < n_scans; ++s)
-            if (h_offsets[s + 1] == h_offsets[s])
-                DSC_CUDA(ctx, cudaMemsetAsync(out + (size_t)s * cells, 0, (size_t)cells * 4, st));
-        if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
-        return DSC_OK;
-    }
-    // ---- shared-memory half grids, one CTA pair per scan, persistent over the batch (A/B variant) ----
-    const size_t hg_smem = (size_t)cells * 2;   // R * S/2 * 4 bytes
-    const bool hg_ok = vec16 && (p->num_sector % 8) == 0 && hg_smem <= ctx->smem_optin &&
-                       (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1 &&
-                       ctx->k1_impl == 2;
-    if (hg_ok) {
-        int pairs = ctx->sm_count / 2;
-        if (pairs > n_scans) pairs = n_scans;
-        unsigned long long *stp = (unsigned long long *)stats;
-#define HG_LAUNCH2(F, V, H, T, U)                                                                               \
-    do {                                                                                                        \
-        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_halfgrid<F, V, H, T, U>,                                          \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hg_smem));         \
-        k1_halfgrid<F, V, H, T, U><<<2 * pairs, T, hg_smem, st>>>(pts, d_offsets, n_scans, out, stp,        \
-                                                                   ctx->pf_dist, cfg);                          \
-    } while (0)
-#define HG_LAUNCH(F, V, H)                                                                                      \
-    do {                                                                                                        \
-        if (ctx->hg_cfg == 1) HG_LAUNCH2(F, V, H, 1024, 3);                                                     \
-        else if (ctx->hg_cfg == 2) HG_LAUNCH2(F, V, H, 512, 4);                                                 \
-        else HG_LAUNCH2(F, V, H, 1024, 2);                                                                      \
-    } while (0)
-        const bool full = p->full_height != 0;
-        if (cfg.fast_ok) {
-            if (p->variant == 0) { if (full) HG_LAUNCH(true, 0, true); else HG_LAUNCH(true, 0, false); }
-            else                 { if (full) HG_LAUNCH(true, 1, true); else HG_LAUNCH(true, 1, false); }
-        } else {
-            if (p->variant == 0) { if (full) HG_LAUNCH(false, 0, true); else HG_LAUNCH(false, 0, false); }
-            else                 { if (full) HG_LAUNCH(false, 1, true); else HG_LAUNCH(false, 1, false); }
-        }
-#undef HG_LAUNCH
-#undef HG_LAUNCH2
-        if ((rc = dsc_check_launch(ctx, "k1_halfgrid"))) return rc;
-        if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
-        return DSC_OK;
-    }
-    // ---- fallback path (small batches, odd grids, 12-byte stride): key grid in L2 + RED.MAX ----
+    // ---- generic path (12-byte stride, odd grids, unaligned buffers): key grid in L2 + RED.MAX, then a decode pass ----
     // key scratch: sized to stay L2-resident between build and decode
     int slots = (int)((size_t)48 * 1024 * 1024 / (size_t)(cells * 4));
     if (slots < 1) slots = 1;
     if (slots > 4096) slots = 4096;
     if (slots > n_scans) slots = n_scans;
-    const size_t need = (size_t)slots * cells * 4;
-    if (need > ctx->keys_bytes) {
-        if (ctx->keys) cudaFree(ctx->keys);
-        ctx->keys = nullptr;
-        ctx->keys_bytes = 0;
-        DSC_CUDA(ctx, cudaMalloc(&ctx->keys, need));
-        ctx->keys_bytes = need;
-        DSC_CUDA(ctx, cudaMemsetAsync(ctx->keys, 0, need, st));
-    }
+    if ((rc = ensure_keys(ctx, (size_t)slots * cells * 4, st))) return rc;
     for (int s0 = 0; s0 < n_scans; s0 += slots) {
         const int g = n_scans - s0 < slots ? n_scans - s0 : slots;
         int64_t max_n = 0;
@@ -474,26 +307,29 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     return DSC_OK;
 }
 
-static int upload_offsets(dsc_ctx *ctx, const int64_t *offsets, int n_scans, cudaStream_t st)
+// Offsets of a device-mode call: a small ring of pinned + device buffer pairs, each guarded by the event of the call
+// that used it last, so that back-to-back asynchronous calls never wait for one another on the host.
+int dsc_upload_offsets(dsc_ctx *ctx, const int64_t *offsets, int n_scans, cudaStream_t st, int *slot_out)
 {
     const size_t cnt = (size_t)n_scans + 1;
-    if (cnt > ctx->d_offsets_cap) {
-        if (ctx->d_offsets) cudaFree(ctx->d_offsets);
-        if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
-        ctx->d_offsets = nullptr;
-        ctx->h_offsets = nullptr;
-        ctx->d_offsets_cap = ctx->h_offsets_cap = 0;
+    const int slot = ctx->off_next;
+    ctx->off_next = (slot + 1) % DSC_OFF_RING;
+    dsc_ctx::OffSlot &o = ctx->off[slot];
+    if (o.used) DSC_CUDA(ctx, cudaEventSynchronize(o.ev));       // DSC_OFF_RING calls ago: long since complete
+    if (cnt > o.cap) {
+        if (o.d) cudaFree(o.d);
+        if (o.h) cudaFreeHost(o.h);
+        o.d = o.h = nullptr;
+        o.cap = 0;
         const size_t cap = cnt < 4096 ? 4096 : cnt * 2;
-        DSC_CUDA(ctx, cudaMalloc(&ctx->d_offsets, cap * sizeof(int64_t)));
-        DSC_CUDA(ctx, cudaMallocHost(&ctx->h_offsets, cap * sizeof(int64_t)));
-        ctx->d_offsets_cap = ctx->h_offsets_cap = cap;
-    } else {
-        // the pinned staging buffer may still be in flight from the previous async call
-        DSC_CUDA(ctx, cudaStreamSynchronize(st));
+        DSC_CUDA(ctx, cudaMalloc(&o.d, cap * sizeof(int64_t)));
+        DSC_CUDA(ctx, cudaMallocHost(&o.h, cap * sizeof(int64_t)));
+        o.cap = cap;
     }
-    memcpy(ctx->h_offsets, offsets, cnt * sizeof(int64_t));
-    DSC_CUDA(ctx, cudaMemcpyAsync(ctx->d_offsets, ctx->h_offsets, cnt * sizeof(int64_t),
-                                  cudaMemcpyHostToDevice, st));
+    if (!o.ev) DSC_CUDA(ctx, cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming));
+    memcpy(o.h, offsets, cnt * sizeof(int64_t));
+    DSC_CUDA(ctx, cudaMemcpyAsync(o.d, o.h, cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    *slot_out = slot;
     return DSC_OK;
 }
 
@@ -522,16 +358,23 @@ void dsc_k1_release(dsc_ctx *ctx)
 {
     free_stage(ctx);
     if (ctx->keys) cudaFree(ctx->keys);
-    if (ctx->d_offsets) cudaFree(ctx->d_offsets);
-    if (ctx->h_offsets) cudaFreeHost(ctx->h_offsets);
+    if (ctx->spill) cudaFree(ctx->spill);
+    for (int i = 0; i < DSC_OFF_RING; ++i) {
+        if (ctx->off[i].d) cudaFree(ctx->off[i].d);
+        if (ctx->off[i].h) cudaFreeHost(ctx->off[i].h);
+        if (ctx->off[i].ev) cudaEventDestroy(ctx->off[i].ev);
+        ctx->off[i] = dsc_ctx::OffSlot();
+    }
     if (ctx->minmax) cudaFree(ctx->minmax);
     if (ctx->sync_buf) cudaFree(ctx->sync_buf);
     ctx->sync_buf = nullptr;
     ctx->sync_cap = 0;
     ctx->keys = nullptr;
-    ctx->d_offsets = nullptr;
-    ctx->h_offsets = nullptr;
+    ctx->keys_bytes = 0;
+    ctx->spill = nullptr;
+    ctx->spill_bytes = 0;
     ctx->minmax = nullptr;
+    ctx->minmax_cap = 0;
 }
 
 // Host-resident batch: chunked, double-buffered pipeline over three streams
@@ -566,6 +409,7 @@ static int build_host(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, con
     }
     int s0 = 0, buf = 0, rc = DSC_OK;
     int used[DSC_NBUF] = {};
+    if ((rc = dsc_enter_stream(ctx, ctx->s_k))) return rc;     // a device-mode call may still be using the engine scratch
     while (s0 < n_scans) {
         int s1 = s0;
         size_t bytes = 0;
@@ -640,11 +484,16 @@ extern "C" int dsc_sc_build_batch(dsc_ctx *ctx, const dsc_params *params, const 
                           out_norm, stats);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = upload_offsets(ctx, offsets, n_scans, st))) return rc;
+    if ((rc = dsc_enter_stream(ctx, st))) return rc;
+    int slot = 0;
+    if ((rc = dsc_upload_offsets(ctx, offsets, n_scans, st, &slot))) return rc;
     if (ctx->timing) DSC_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    rc = build_device(ctx, params, (const uint8_t *)pts, ctx->d_offsets, offsets, n_scans, pts_stride_bytes,
+    rc = build_device(ctx, params, (const uint8_t *)pts, ctx->off[slot].d, offsets, n_scans, pts_stride_bytes,
                       out_grids, out_norm, stats, st);
     if (rc) return rc;
+    DSC_CUDA(ctx, cudaEventRecord(ctx->off[slot].ev, st));
+    ctx->off[slot].used = 1;
+    if ((rc = dsc_leave_stream(ctx, st))) return rc;
     if (ctx->timing) {
         DSC_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
         DSC_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -661,12 +510,17 @@ extern "C" int dsc_sc_normalize01(dsc_ctx *ctx, const float *grids, int n_grids,
     if (n_grids == 0) return DSC_OK;
     if (!grids || !out) DSC_FAIL(ctx, DSC_ERR_INVALID, "NULL buffer");
     DSC_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (mem == DSC_MEM_DEVICE) return normalize_device(ctx, grids, n_grids, cells_per_grid, out, (cudaStream_t)stream);
-    const size_t bytes = (size_t)n_grids * cells_per_grid * 4;
     int rc;
+    if (mem == DSC_MEM_DEVICE) {
+        if ((rc = dsc_enter_stream(ctx, (cudaStream_t)stream))) return rc;
+        if ((rc = normalize_device(ctx, grids, n_grids, cells_per_grid, out, (cudaStream_t)stream))) return rc;
+        return dsc_leave_stream(ctx, (cudaStream_t)stream);
+    }
+    const size_t bytes = (size_t)n_grids * cells_per_grid * 4;
     if ((rc = dsc_reserve_scratch(ctx, bytes * 2))) return rc;
     float *d_in = (float *)ctx->scratch, *d_out = d_in + (size_t)n_grids * cells_per_grid;
     cudaStream_t st = ctx->s_k;
+    if ((rc = dsc_enter_stream(ctx, st))) return rc;
     DSC_CUDA(ctx, cudaMemcpyAsync(d_in, grids, bytes, cudaMemcpyHostToDevice, st));
     if ((rc = normalize_device(ctx, d_in, n_grids, cells_per_grid, d_out, st))) return rc;
     DSC_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st));

@@ -4,16 +4,27 @@
 
 // ---- K1 main path: persistent CTAs, one work item (a scan, or a slice of a big scan) at a time ------------------
 // A CTA streams the item's points once (128-bit loads, two register sets ping-pong), bins each point once and
-// folds it into the key grid: the hot ring rows live in shared memory (LDS pre-check + ATOMS.MAX), the other rows
-// in the CTA's private L2-resident slot (RED.MAX, fire and forget).  When a scan is done the same CTA decodes
-// rows and slot to floats (coalesced 128-bit streaming stores) and re-zeroes both.  There is no synchronisation
-// between CTAs for whole-scan items; HBM sees each point once and each output cell once.
+// folds it into the key grid.  The 460 KB grid does not fit one SM, so the reduction runs in ring bands:
+//   pass 1 (the stream)  the hot ring rows -- rings 0 .. ns-2 and the clamp ring R-1, 75-90 % of the points of a
+//                        KITTI-like scan -- live in shared memory (LDS pre-check + ATOMS.MAX).  A point of any other
+//                        ring is NOT reduced yet: its (cell, key) pair is appended to the warp's private spill list
+//                        (one ballot, one coalesced 8-byte store per lane; the list is a few hundred KB per CTA and
+//                        stays in L2).
+//   write-out            the resident rows are decoded to floats (coalesced 128-bit streaming stores) and re-zeroed;
+//   pass 2 (per band)    the same shared-memory rows now stand for the next band of up to ns rings: every warp
+//                        re-reads its own spill list (L2 hits, 128-bit loads) and folds the band's entries in with
+//                        the same LDS pre-check + ATOMS.MAX; the band is decoded and written out; repeat until
+//                        ring R-2.
+// So every max-reduction is a shared-memory atomic, HBM sees each point once and each output cell once, there are
+// no global atomics, no key slots to read back and re-zero, and no synchronisation between CTAs for whole-scan items.
+// (Round 1 reduced the non-resident rings with RED.MAX on a private L2 slot per CTA: 72 M scattered L2 atomics per
+// launch, a 282 KB read-back + re-zero per scan and 1.2x write traffic from evicted slot lines: profiles/r1_notes.md.)
 constexpr int SC_THREADS = 1024;
-#ifndef SC_TOUCH
-#define SC_TOUCH 0                    // 1: touched-segment flags for the L2-row decode (measured: slower, see r1_notes.md)
-#endif
 #ifndef SC_DU
-#define SC_DU 4                       // 128-bit L2 loads in flight per thread in the decode
+#define SC_DU 4                       // 128-bit L2 loads in flight per thread in the split-mode decode
+#endif
+#ifndef SC_LU
+#define SC_LU 4                       // 128-bit spill-list loads in flight per lane in pass 2
 #endif
 
 // SPLIT = true: a scan is cut into `parts` contiguous point ranges (work items) that different CTAs
@@ -48,85 +59,106 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
-
-// fold one binned point into the key grid: resident rows -> LDS pre-check + ATOMS.MAX, other rows -> RED.MAX (L2)
-// The L2 rows of a scan are sparse (5-25 % of their cells ever see a point), yet the decode has to read every
-// key back through a ~1 us round trip.  TOUCH: remember which 16-cell segments received a RED (one byte flag per
-// segment in shared memory, plain store), so that the decode reads -- and re-zeroes -- only those.
-constexpr int SC_SEG_SHIFT = 4;                               // 16 cells = 64 B = 4 x 128-bit per segment
-// The flags sit right below the resident rows, one byte per segment of the WHOLE grid and indexed by the
-// absolute cell number, so the hot path needs no extra base register: flag(cell) = rows_base - bytes + (cell >> 4).
-__host__ __device__ constexpr uint32_t sc_flag_bytes(int cells) { return ((uint32_t)(cells >> SC_SEG_SHIFT) + 1u + 127u) & ~127u; }
-
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
+__device__ __forceinline__ unsigned lanemask_lt()
 {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+// spill-list traffic goes to L2 and no further (st.cg / ld.cg): written once, read back by the same SM
+__device__ __forceinline__ void st_spill(uint2 *p, uint32_t cell, uint32_t key)
 {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    asm volatile("st.global.cg.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(cell), "r"(key) : "memory");
+}
+__device__ __forceinline__ uint4 ld_spill2(const uint2 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
-template <bool FULL, bool TOUCH>
-__device__ __forceinline__ void sc_update(const float zv, const int cell, uint32_t *__restrict__ grid, const SmemRows sm,
-                                          const uint32_t flag_bytes)
+// Fold one binned point into the key grid.  Called warp-uniformly; `valid` masks lanes without a point.
+//   resident cell      LDS pre-check + ATOMS.MAX (most points are not a new maximum)
+//   any other cell     SPILL: appended to the warp's spill list (`gp` is the list's write pointer, advanced for the whole
+//                      warp);  !SPILL (split items): RED.MAX straight into the scan's key grid (`gp` is that grid)
+template <bool FULL, bool SPILL>
+__device__ __forceinline__ void sc_commit(const float zv, const int cell, bool valid, const SmemRows sm, uint32_t *&gp)
 {
     const uint32_t u = __float_as_uint(zv);
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
-    if (zv != zv) return;                        // NaN never wins (scaner_version2.py:107)
-    if (!FULL && !(zv > 0.0f)) return;           // offset mode: cells start at 0, strict '>'
-    if (cell < sm.lim || cell >= sm.last) {
+    valid = valid && (zv == zv);                 // NaN never wins (scaner_version2.py:107)
+    if (!FULL) valid = valid && (zv > 0.0f);     // offset mode: cells start at 0, strict '>'
+    const bool res = cell < sm.lim || cell >= sm.last;
+    if (valid && res) {
         const int local = cell < sm.lim ? cell : cell + sm.shift;               // clamp ring -> row ns-1
         const uint32_t addr = sm.base + (uint32_t)local * 4u;
-        if (key > lds_u32(addr)) reds_max_u32(addr, key);   // most points are not a new maximum
-        return;
+        if (key > lds_u32(addr)) reds_max_u32(addr, key);
     }
-    red_max_global(grid + cell, key);
-    if constexpr (TOUCH) sts_u8(sm.base - flag_bytes + (uint32_t)(cell >> SC_SEG_SHIFT), 1u);
+    if constexpr (SPILL) {
+        const unsigned m = __ballot_sync(0xffffffffu, valid && !res);
+        if (m) {                                 // warp-uniform
+            uint2 *w = reinterpret_cast<uint2 *>(gp);
+            if (valid && !res) st_spill(w + __popc(m & lanemask_lt()), (uint32_t)cell, key);
+            gp = reinterpret_cast<uint32_t *>(w + __popc(m));
+        }
+    } else {
+        if (valid && !res) red_max_global(gp + cell, key);
+    }
 }
 
-// exact chain for one queued point (entry address of this lane); returns 1 if the point was clamped into the last ring
-template <int VARIANT, bool FULL, bool TOUCH>
-__device__ __noinline__ unsigned sc_exact_queued(uint32_t qaddr, const ExactArgs *__restrict__ ea,
-                                                 uint32_t *__restrict__ grid, uint32_t sm_base, int sm_lim, int sm_last,
-                                                 uint32_t flag_bytes, unsigned long long *__restrict__ st)
+// exact chain for one queued point (entry address of this lane): packed result of hg_bin_exact, counters updated
+template <int VARIANT, bool FULL>
+__device__ __noinline__ uint2 sc_exact_queued(uint32_t qaddr, const ExactArgs *__restrict__ ea,
+                                              unsigned long long *__restrict__ st)
 {
     const float x = lds_f32(qaddr), y = lds_f32(qaddr + SCQ_CAP * 4), z = lds_f32(qaddr + SCQ_CAP * 8);
     const uint2 b = hg_bin_exact<VARIANT, FULL>(x, y, z, ea);
-    const int status = (int)(b.x >> 27), cell = (int)(b.x & 0x7ffffffu);
+    const int status = (int)(b.x >> 27);
     if (st) {                                    // rare events: straight to the per-scan counters
         atomicAdd(st + 5, 1ull);
         if (status == dsc::PT_NONFINITE) atomicAdd(st + 1, 1ull);
         if (status == dsc::PT_SECTOR_OVERFLOW) atomicAdd(st + 2, 1ull);
         if (status == dsc::PT_OUT_OF_RANGE) atomicAdd(st + 4, 1ull);
     }
-    if (status > dsc::PT_CLAMPED) return 0u;
-    sc_update<FULL, TOUCH>(__uint_as_float(b.y), cell, grid, SmemRows{sm_base, sm_lim, sm_last, sm_lim - sm_last}, flag_bytes);
-    return status == dsc::PT_CLAMPED ? 1u : 0u;
+    return b;
+}
+
+// run the exact chain for the queue entries [first, first + count) of this warp (count <= 32) and commit them
+template <int VARIANT, bool FULL, bool SPILL>
+__device__ __forceinline__ void sc_exact_batch(const uint32_t queue, const unsigned first, const unsigned count,
+                                               const ExactArgs *ea, uint32_t *&gp, unsigned &n_clamped,
+                                               unsigned long long *__restrict__ st, const SmemRows sm)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const bool mine = lane < count;
+    uint2 b = make_uint2((uint32_t)dsc::PT_NONFINITE << 27, 0u);
+    __syncwarp();
+    if (mine) b = sc_exact_queued<VARIANT, FULL>(queue + (first + lane) * 4u, ea, st);
+    __syncwarp();
+    const int status = (int)(b.x >> 27);
+    n_clamped += (mine && status == dsc::PT_CLAMPED) ? 1u : 0u;
+    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED, sm, gp);
 }
 
 // One point per lane, called warp-uniformly (`active` masks lanes past the end of the item).
-template <int VARIANT, bool FULL, bool DEF, bool TOUCH>
+template <int VARIANT, bool FULL, bool DEF, bool SPILL>
 __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v, const bool active,
-                                         uint32_t *__restrict__ grid, unsigned &n_clamped,
-                                         unsigned long long *__restrict__ st, const SmemRows sm,
-                                         const uint32_t queue, unsigned &qcount, const uint32_t flag_bytes)
+                                         uint32_t *&gp, unsigned &n_clamped, unsigned long long *__restrict__ st,
+                                         const SmemRows sm, const uint32_t queue, unsigned &qcount)
 {
     int ring, sector;
     bool beyond;
     bool ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
     if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
-    if (ok && active) {
-        if (VARIANT == 1 && beyond) {
-            if (st) atomicAdd(st + 4, 1ull);
-        } else {
-            if (VARIANT == 0) n_clamped += beyond;
-            const int S = DEF ? dsc::defgrid::S : cfg.S;
-            sc_update<FULL, TOUCH>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, grid, sm, flag_bytes);
-        }
+    bool take = ok && active;
+    if (VARIANT == 1) {
+        if (take && beyond && st) atomicAdd(st + 4, 1ull);   // r > max_length: dropped (scan_context_node.py:134-137)
+        take = take && !beyond;
+    } else {
+        n_clamped += (take && beyond) ? 1u : 0u;
     }
+    const int S = DEF ? dsc::defgrid::S : cfg.S;
+    sc_commit<FULL, SPILL>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, take, sm, gp);
     const unsigned m = __ballot_sync(0xffffffffu, active && !ok);
     if (m) {                                     // warp-uniform, rare
         const unsigned lane = threadIdx.x & 31u;
@@ -139,25 +171,40 @@ __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea,
         qcount += __popc(m);
         if (qcount >= 32u) {
             qcount -= 32u;
-            __syncwarp();
-            n_clamped += sc_exact_queued<VARIANT, FULL, TOUCH>(queue + (qcount + lane) * 4u, ea, grid, sm.base, sm.lim, sm.last, flag_bytes, st);
-            __syncwarp();
+            sc_exact_batch<VARIANT, FULL, SPILL>(queue, qcount, 32u, ea, gp, n_clamped, st, sm);
         }
     }
 }
 
-// end of item: the queue's remaining entries (fewer than 32)
-template <int VARIANT, bool FULL, bool TOUCH>
-__device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *__restrict__ grid, unsigned &n_clamped,
-                                         unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t queue,
-                                         unsigned &qcount, const uint32_t flag_bytes)
+// exact-only flavour (DSC_FLAG_EXACT_ONLY, non-dyadic gaps): every point takes the fdlibm chain
+template <int VARIANT, bool FULL, bool SPILL>
+__device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4 v, const bool active, uint32_t *&gp,
+                                               unsigned &n_clamped, unsigned long long *__restrict__ st, const SmemRows sm)
 {
-    if (qcount) {
-        const unsigned lane = threadIdx.x & 31u;
-        __syncwarp();
-        if (lane < qcount)
-            n_clamped += sc_exact_queued<VARIANT, FULL, TOUCH>(queue + lane * 4u, ea, grid, sm.base, sm.lim, sm.last, flag_bytes, st);
-        __syncwarp();
+    uint2 b = make_uint2((uint32_t)dsc::PT_NONFINITE << 27, 0u);
+    if (active) {
+        b = hg_bin_exact<VARIANT, FULL>(v.x, v.y, v.z, ea);
+        const int status = (int)(b.x >> 27);
+        if (st && status > dsc::PT_CLAMPED) {
+            if (status == dsc::PT_NONFINITE) atomicAdd(st + 1, 1ull);
+            if (status == dsc::PT_SECTOR_OVERFLOW) atomicAdd(st + 2, 1ull);
+            if (status == dsc::PT_OUT_OF_RANGE) atomicAdd(st + 4, 1ull);
+        }
+    }
+    __syncwarp();
+    const int status = (int)(b.x >> 27);
+    n_clamped += (active && status == dsc::PT_CLAMPED) ? 1u : 0u;
+    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), active && status <= dsc::PT_CLAMPED, sm, gp);
+}
+
+// end of item: the queue's remaining entries (fewer than 32)
+template <int VARIANT, bool FULL, bool SPILL>
+__device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *&gp, unsigned &n_clamped,
+                                         unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t queue,
+                                         unsigned &qcount)
+{
+    if (qcount) {                                // warp-uniform
+        sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gp, n_clamped, st, sm);
         qcount = 0;
     }
 }
@@ -185,152 +232,139 @@ __device__ __forceinline__ void sc_item(int item, const int64_t *__restrict__ of
     }
 }
 
-// End of a work item.  Non-split: this CTA owns the whole scan -- decode the resident rows and the private
-// L2 slot to floats (coalesced 128-bit streaming stores) and re-zero both.  Split: fold the resident rows
-// into the scan's key grid (== its output grid), count the item as retired, and if it was the scan's last
-// item decode the grid in place.  Ends with a CTA barrier in both cases.
-template <bool SPLIT, int NT, int DU = 4>
-__device__ __forceinline__ void sc_finish_item(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid,
-                                               float *__restrict__ out_scan, int ns, int R, int S, int scan, int parts,
-                                               unsigned int *__restrict__ done, int *s_last,
-                                               unsigned int *__restrict__ reset = nullptr, const uint32_t flags = 0u)
+__device__ __forceinline__ float4 sc_decode4(const uint4 q)
+{
+    float4 f;
+    f.x = dsc::key_to_float(q.x);
+    f.y = dsc::key_to_float(q.y);
+    f.z = dsc::key_to_float(q.z);
+    f.w = dsc::key_to_float(q.w);
+    return f;
+}
+
+// decode `nvec` 128-bit groups of keys from shared memory to floats, re-zeroing the rows
+template <int NT>
+__device__ __forceinline__ void sc_flush_rows(uint32_t *__restrict__ srows, float4 *__restrict__ dst, int nvec)
+{
+    for (int i = threadIdx.x; i < nvec; i += NT) {
+        const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
+        reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+        __stcs(dst + i, sc_decode4(q));
+    }
+}
+
+// End of a whole-scan item (this CTA owns the scan): write out the resident rows, then reduce and write out the other
+// rings band by band from the spill lists.  `wseg`/`wend`: this warp's list.  Ends with a CTA barrier.
+template <int NT>
+__device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, const uint32_t sbase,
+                                               float *__restrict__ out_scan, const int ns, const int R, const int S,
+                                               const uint2 *__restrict__ wseg, const uint2 *__restrict__ wend)
+{
+    const int rowvec = S >> 2;
+    float4 *oq = reinterpret_cast<float4 *>(out_scan);
+    __syncthreads();                             // every shared-memory atomic and every list store of the item is done
+    // resident rows: rings 0 .. ns-2, and the clamp ring R-1 kept in row ns-1
+    sc_flush_rows<NT>(srows, oq, (ns - 1) * rowvec);
+    for (int i = threadIdx.x; i < rowvec; i += NT) {
+        uint4 *src = reinterpret_cast<uint4 *>(srows) + (ns - 1) * rowvec + i;
+        const uint4 q = *src;
+        *src = make_uint4(0, 0, 0, 0);
+        __stcs(oq + (size_t)(R - 1) * rowvec + i, sc_decode4(q));
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    for (int row0 = ns - 1; row0 < R - 1; row0 += ns) {         // bands of up to ns rings
+        const int rows = R - 1 - row0 < ns ? R - 1 - row0 : ns;
+        const uint32_t c_lo = (uint32_t)row0 * (uint32_t)S, c_n = (uint32_t)rows * (uint32_t)S;
+        __syncthreads();                         // the rows are zero again
+        // this warp's list, two entries per 128-bit load, SC_LU loads in flight per lane
+        for (const uint2 *e0 = wseg + 2u * lane; e0 < wend; e0 += 64 * SC_LU) {
+            uint4 q[SC_LU];
+#pragma unroll
+            for (int d = 0; d < SC_LU; ++d) {
+                const uint2 *e = e0 + 64 * d;
+                if (e < wend) q[d] = ld_spill2(e);
+            }
+#pragma unroll
+            for (int d = 0; d < SC_LU; ++d) {
+                const uint2 *e = e0 + 64 * d;
+                if (e < wend) {
+                    const uint32_t l0 = q[d].x - c_lo;
+                    if (l0 < c_n) {
+                        const uint32_t a = sbase + l0 * 4u;
+                        if (q[d].y > lds_u32(a)) reds_max_u32(a, q[d].y);
+                    }
+                    const uint32_t l1 = q[d].z - c_lo;
+                    if (e + 1 < wend && l1 < c_n) {
+                        const uint32_t a = sbase + l1 * 4u;
+                        if (q[d].w > lds_u32(a)) reds_max_u32(a, q[d].w);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        sc_flush_rows<NT>(srows, oq + (size_t)row0 * rowvec, rows * rowvec);
+    }
+    __syncthreads();                             // rows are zero before the next scan's atomics
+}
+
+// End of a split work item: fold the resident rows into the scan's key grid (== its output grid), count the item as
+// retired, and if it was the scan's last item decode the grid in place.  Ends with a CTA barrier.
+template <int NT, int DU = 4>
+__device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid, int ns, int R,
+                                                int S, int scan, int parts, unsigned int *__restrict__ done, int *s_last)
 {
     const int tid = threadIdx.x;
     const int rowvec = S >> 2;
     const int cells = R * S;
     const int nres = ns * rowvec;
     const int lim = (ns - 1) * rowvec, shift = (R - ns) * rowvec;    // resident row ns-1 holds ring R-1
-    if constexpr (SPLIT) {
-        __syncthreads();                         // every shared-memory atomic of the item has landed
-        for (int i = tid; i < nres; i += NT) {
-            const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
-            if ((q.x | q.y | q.z | q.w) == 0u) continue;
-            reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
-            uint32_t *g = grid + 4 * (size_t)(i < lim ? i : i + shift);
-            if (q.x) red_max_global(g + 0, q.x);
-            if (q.y) red_max_global(g + 1, q.y);
-            if (q.z) red_max_global(g + 2, q.z);
-            if (q.w) red_max_global(g + 3, q.w);
-        }
-        __threadfence();                         // release: this CTA's REDs are performed ...
-        __syncthreads();
-        if (tid == 0) {
-            if (reset) *reset = 0u;              // every warp has left the item's streaming loop
-            const unsigned prev = atomicAdd(done + scan, 1u);          // ... before the item counts as retired
-            *s_last = prev + 1u == (unsigned)parts;
-            if (prev + 1u == (unsigned)parts) __threadfence();         // acquire: the other CTAs' REDs are visible
-        }
-        __syncthreads();
-        if (*s_last) {
-            uint4 *kq = reinterpret_cast<uint4 *>(grid);
-            const int nvec = cells >> 2;
-            for (int i0 = tid; i0 < nvec; i0 += NT * DU) {
-                uint4 q[DU];
-#pragma unroll
-                for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * NT;
-                    if (i < nvec) q[d] = __ldcg(kq + i);
-                }
-#pragma unroll
-                for (int d = 0; d < DU; ++d) {
-                    const int i = i0 + d * NT;
-                    if (i < nvec) {
-                        float4 f;
-                        f.x = dsc::key_to_float(q[d].x);
-                        f.y = dsc::key_to_float(q[d].y);
-                        f.z = dsc::key_to_float(q[d].z);
-                        f.w = dsc::key_to_float(q[d].w);
-                        __stcs(reinterpret_cast<float4 *>(kq) + i, f);
-                    }
-                }
-            }
-        }
-        __syncthreads();                         // s_last is rewritten by the next item
-    } else {
-        __threadfence();                         // our REDs are performed ...
-        __syncthreads();                         // ... before any thread of the CTA reads the keys back
-        if (tid == 0 && reset) *reset = 0u;      // every warp has left the item's streaming loop
-        float4 *oq = reinterpret_cast<float4 *>(out_scan);
-        for (int i = tid; i < nres; i += NT) {       // resident rows: rings 0 .. ns-2 and the clamp ring
-            const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
-            reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
-            float4 f;
-            f.x = dsc::key_to_float(q.x);
-            f.y = dsc::key_to_float(q.y);
-            f.z = dsc::key_to_float(q.z);
-            f.w = dsc::key_to_float(q.w);
-            __stcs(oq + (i < lim ? i : i + shift), f);
-        }
-        if (ns < R) {                            // L2 rows: rings ns-1 .. R-2
-            const uint4 *kq = reinterpret_cast<const uint4 *>(grid);
-            uint4 *kz = reinterpret_cast<uint4 *>(grid);
-            const int lo = (ns > 0 ? ns - 1 : 0) * rowvec, hi = (ns > 0 ? R - 1 : R) * rowvec;
-            if (flags) {
-                // only the segments that received a RED are read back (and re-zeroed); the rest is written as zeros
-                for (int i0 = lo + tid; i0 < hi; i0 += NT * DU) {
-                    uint4 q[DU];
-                    bool t[DU];
-#pragma unroll
-                    for (int d = 0; d < DU; ++d) {
-                        const int i = i0 + d * NT;
-                        t[d] = i < hi && lds_u8(flags + (uint32_t)(i >> (SC_SEG_SHIFT - 2))) != 0u;
-                        if (t[d]) q[d] = __ldcg(kq + i);
-                    }
-#pragma unroll
-                    for (int d = 0; d < DU; ++d) {
-                        const int i = i0 + d * NT;
-                        if (i < hi) {
-                            float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                            if (t[d]) {
-                                f.x = dsc::key_to_float(q[d].x);
-                                f.y = dsc::key_to_float(q[d].y);
-                                f.z = dsc::key_to_float(q[d].z);
-                                f.w = dsc::key_to_float(q[d].w);
-                                __stcg(kz + i, make_uint4(0, 0, 0, 0));
-                            }
-                            __stcs(oq + i, f);
-                        }
-                    }
-                }
-                __syncthreads();                 // every flag has been read ...
-                const int nseg4 = (int)(sc_flag_bytes(R * S) >> 2);                      // flags, in 32-bit words
-                for (int i = tid; i < nseg4; i += NT)
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(flags + (uint32_t)i * 4u), "r"(0u) : "memory");
-            } else {
-                for (int i0 = lo + tid; i0 < hi; i0 += NT * DU) {
-                    uint4 q[DU];
-#pragma unroll
-                    for (int d = 0; d < DU; ++d) {
-                        const int i = i0 + d * NT;
-                        if (i < hi) q[d] = __ldcg(kq + i);
-                    }
-#pragma unroll
-                    for (int d = 0; d < DU; ++d) {
-                        const int i = i0 + d * NT;
-                        if (i < hi) {
-                            float4 f;
-                            f.x = dsc::key_to_float(q[d].x);
-                            f.y = dsc::key_to_float(q[d].y);
-                            f.z = dsc::key_to_float(q[d].z);
-                            f.w = dsc::key_to_float(q[d].w);
-                            __stcs(oq + i, f);
-                            __stcg(kz + i, make_uint4(0, 0, 0, 0));
-                        }
-                    }
-                }
-            }
-        }
-        __threadfence();                         // the zeroes are performed ...
-        __syncthreads();                         // ... before the next scan's REDs
+    __syncthreads();                             // every shared-memory atomic of the item has landed
+    for (int i = tid; i < nres; i += NT) {
+        const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
+        if ((q.x | q.y | q.z | q.w) == 0u) continue;
+        reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+        uint32_t *g = grid + 4 * (size_t)(i < lim ? i : i + shift);
+        if (q.x) red_max_global(g + 0, q.x);
+        if (q.y) red_max_global(g + 1, q.y);
+        if (q.z) red_max_global(g + 2, q.z);
+        if (q.w) red_max_global(g + 3, q.w);
     }
+    __threadfence();                             // release: this CTA's REDs are performed ...
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned prev = atomicAdd(done + scan, 1u);          // ... before the item counts as retired
+        *s_last = prev + 1u == (unsigned)parts;
+        if (prev + 1u == (unsigned)parts) __threadfence();         // acquire: the other CTAs' REDs are visible
+    }
+    __syncthreads();
+    if (*s_last) {
+        uint4 *kq = reinterpret_cast<uint4 *>(grid);
+        const int nvec = cells >> 2;
+        for (int i0 = tid; i0 < nvec; i0 += NT * DU) {
+            uint4 q[DU];
+#pragma unroll
+            for (int d = 0; d < DU; ++d) {
+                const int i = i0 + d * NT;
+                if (i < nvec) q[d] = __ldcg(kq + i);
+            }
+#pragma unroll
+            for (int d = 0; d < DU; ++d) {
+                const int i = i0 + d * NT;
+                if (i < nvec) __stcs(reinterpret_cast<float4 *>(kq) + i, sc_decode4(q[d]));
+            }
+        }
+    }
+    __syncthreads();                             // s_last is rewritten by the next item
 }
 
 // (A flavour with the resident-row count as a template constant -- row-placement tests and clamp-row shift as
 // immediates -- was measured 10 % SLOWER than this one, which takes `ns` at run time: profiles/r1_notes.md.)
+//   spill       whole-scan items: [gridDim.x][spill_cap] (cell, key) pairs, one region per CTA, cut into per-warp lists
+//   spill_cap   entries per CTA: >= ceil(max points per scan / NT) * NT
 template <bool FAST, int VARIANT, bool FULL, int U, int NT, bool DEF, bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
-        uint32_t *__restrict__ keys, float *__restrict__ out, unsigned long long *__restrict__ stats,
+        uint2 *__restrict__ spill, const size_t spill_cap, float *__restrict__ out, unsigned long long *__restrict__ stats,
         unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg, const SplitArgs sp)
 {
     // NB: this kernel lives on the edge of its register budget (64 regs at 1024 threads, 80 at 768); measured
@@ -338,6 +372,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     // per-warp chunk counters, 8 decode loads in flight) spilled inside the loop and lost 15-40 %
     // (profiles/r1_notes.md).
     constexpr int STEP = NT * U;
+    constexpr bool SPILL = !SPLIT;
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ int s_next[2];
     __shared__ int s_last;
@@ -346,23 +381,17 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int R = DEF ? dsc::defgrid::R : cfg.R, S = DEF ? dsc::defgrid::S : cfg.S;
     const int cells = R * S;
     const int rowvec = S >> 2;                   // host guarantees S % 4 == 0
-    // private L2 slot of this CTA: only the non-resident rows exist in it; the pointer is biased so that it is still
-    // indexed by the absolute cell number
-    uint32_t *grid = SPLIT ? nullptr
-                           : keys + (size_t)blockIdx.x * (size_t)((ns > 0 ? R - ns : R) * S) - (ns > 0 ? (ns - 1) * S : 0);
     const uint64_t pol_stream = l2_policy_evict_first();
-    // dynamic shared memory: [touched-segment flags (TOUCH only)][ns ring rows of keys][per-warp exact-path queues]
-    constexpr bool TOUCH = SC_TOUCH && FAST && !SPLIT;       // whole-scan items of the screened kernels
-    const uint32_t flag_bytes = TOUCH ? sc_flag_bytes(cells) : 0u;
-    uint32_t *const srows = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem_raw) + flag_bytes);
+    // dynamic shared memory: [ns ring rows of keys][per-warp exact-path queues]
+    uint32_t *const srows = smem_raw;
     SmemRows sm;
     sm.base = (uint32_t)__cvta_generic_to_shared(srows);
-    sm.lim = ns > 0 ? (ns - 1) * S : 0;
-    sm.last = ns > 0 ? (R - 1) * S : 0x7fffffff;
+    sm.lim = (ns - 1) * S;                       // host guarantees ns >= 2
+    sm.last = (R - 1) * S;
     sm.shift = sm.lim - sm.last;
     const uint32_t queue = sm.base + (uint32_t)ns * (uint32_t)S * 4u + (uint32_t)(tid >> 5) * SCQ_WARP_BYTES;
     unsigned qcount = 0;
-    for (int i = tid; i < (int)(flag_bytes >> 4) + ns * rowvec; i += NT) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < ns * rowvec; i += NT) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         fill_exact_args(&s_ea, cfg);
         s_next[0] = (int)atomicAdd(cursor, 1u);
@@ -377,18 +406,27 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
         int scan, parts, n;
         int64_t p0;
         sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
-        if constexpr (SPLIT) grid = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
+        // gp: split items -- the scan's key grid (== its output grid); whole scans -- write pointer of this warp's spill list
+        uint32_t *gp;
+        const uint2 *wseg = nullptr;
+        if constexpr (SPLIT) {
+            gp = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
+        } else {
+            const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;           // most points one warp can see
+            wseg = spill + (size_t)blockIdx.x * spill_cap + (size_t)(tid >> 5) * seg;
+            gp = reinterpret_cast<uint32_t *>(const_cast<uint2 *>(wseg));
+        }
         const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
         unsigned n_clamped = 0;
-        unsigned long long *st = stats ? stats + (int64_t)scan * 6 : nullptr;
+        unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
         const int nfull = n / STEP;
         const float4 *p = s4 + tid;
         float4 a[U], b[U];
 #define SC_LD(ptr) ld_stream_f4_hint((ptr), pol_stream)
 #define SC_PT(v, act)                                                                                           \
     do {                                                                                                        \
-        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, TOUCH>(cfg, &s_ea, (v), (act), grid, n_clamped, st, sm, queue, qcount, flag_bytes); \
-        else if (act) st_point<false, VARIANT, FULL, DEF, true>(cfg, &s_ea, (v), grid, n_clamped, stats, scan, 0, sm);   \
+        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, SPILL>(cfg, &s_ea, (v), (act), gp, n_clamped, st, sm, queue, qcount); \
+        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v), (act), gp, n_clamped, st, sm);                   \
     } while (0)
         if (nfull > 0) {
 #pragma unroll
@@ -419,7 +457,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             if (act) v = SC_LD(s4 + i0 + tid);
             SC_PT(v, act);
         }
-        if constexpr (FAST) sc_drain<VARIANT, FULL, TOUCH>(&s_ea, grid, n_clamped, st, sm, queue, qcount, flag_bytes);
+        if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gp, n_clamped, st, sm, queue, qcount);
 #undef SC_LD
 #undef SC_PT
         if (stats) {
@@ -427,9 +465,11 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
             if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
         }
-        sc_finish_item<SPLIT, NT, SC_DU>(srows, grid, out + (size_t)scan * cells, ns, R, S, scan, parts, sp.done, &s_last,
-                                         nullptr, TOUCH ? sm.base - flag_bytes : 0u);
+        if constexpr (SPLIT)
+            sc_finish_split<NT, SC_DU>(srows, gp, ns, R, S, scan, parts, sp.done, &s_last);
+        else
+            sc_finish_scan<NT>(srows, sm.base, out + (size_t)scan * cells, ns, R, S, wseg, reinterpret_cast<const uint2 *>(gp));
         par ^= 1;
-        item = s_next[par];                      // published by the barriers of sc_finish_item
+        item = s_next[par];                      // published by the barriers of the finish
     }
 }

@@ -439,6 +439,7 @@ extern "C" int dsc_raster_boxes(dsc_ctx *ctx, const double *boxes, int n_boxes, 
     const int R = ctx->tab_R, S = ctx->tab_S;
     const bool host = mem == DSC_MEM_HOST;
     cudaStream_t st = host ? ctx->s_k : (cudaStream_t)stream;
+    if ((rc = dsc_enter_stream(ctx, st))) return rc;
     const int64_t n_rows = (int64_t)n_boxes * R;
     // scratch layout
     size_t o = 0;
@@ -473,7 +474,7 @@ extern "C" int dsc_raster_boxes(dsc_ctx *ctx, const double *boxes, int n_boxes, 
                                                          row_counts, row_offsets, d_cells, cap, d_dense);
         if ((rc = dsc_check_launch(ctx, "k2_rows<write>"))) return rc;
     }
-    if (!host) return DSC_OK;
+    if (!host) return dsc_leave_stream(ctx, st);
     DSC_CUDA(ctx, cudaMemcpyAsync(cell_offsets, item_offsets, (size_t)(n_boxes + 1) * 8, cudaMemcpyDeviceToHost, st));
     DSC_CUDA(ctx, cudaStreamSynchronize(st));
     const int64_t total = cell_offsets[n_boxes];
@@ -504,6 +505,7 @@ extern "C" int dsc_reconstruct_batch(dsc_ctx *ctx, const float *grids, int n_gri
     const int64_t cells = (int64_t)R * S;
     const bool host = mem == DSC_MEM_HOST;
     cudaStream_t st = host ? ctx->s_k : (cudaStream_t)stream;
+    if ((rc = dsc_enter_stream(ctx, st))) return rc;
     const int64_t n_rows = (int64_t)n_grids * R;
     size_t o = 0;
     const size_t o_counts = o;   o = align_up(o + (size_t)(n_rows + 1) * 4, 256);
@@ -560,7 +562,7 @@ extern "C" int dsc_reconstruct_batch(dsc_ctx *ctx, const float *grids, int n_gri
         if ((rc = dsc_check_launch(ctx, "k3_rows<write>"))) return rc;
         }
     }
-    if (!host) return DSC_OK;
+    if (!host) return dsc_leave_stream(ctx, st);
     DSC_CUDA(ctx, cudaMemcpyAsync(pt_offsets, item_offsets, (size_t)(n_grids + 1) * 8, cudaMemcpyDeviceToHost, st));
     DSC_CUDA(ctx, cudaStreamSynchronize(st));
     const int64_t total = pt_offsets[n_grids];
@@ -592,6 +594,7 @@ extern "C" int dsc_covered_mask(dsc_ctx *ctx, const int32_t *bin_ids, int64_t n_
     const size_t bits_bytes = align_up((size_t)(total_cells + 31) / 32 * 4, 256);
     const bool host = mem == DSC_MEM_HOST;
     cudaStream_t st = host ? ctx->s_k : (cudaStream_t)stream;
+    if ((rc = dsc_enter_stream(ctx, st))) return rc;
     size_t o = bits_bytes;
     const size_t o_ids = o;    o = align_up(o + (host ? (size_t)n_ids * 4 : 0), 256);
     const size_t o_cells = o;  o = align_up(o + (host ? (size_t)n_cells * 8 : 0), 256);
@@ -616,8 +619,9 @@ extern "C" int dsc_covered_mask(dsc_ctx *ctx, const int32_t *bin_ids, int64_t n_
     if (host) {
         DSC_CUDA(ctx, cudaMemcpyAsync(mask_out, d_mask, (size_t)n_ids, cudaMemcpyDeviceToHost, st));
         DSC_CUDA(ctx, cudaStreamSynchronize(st));
+        return DSC_OK;
     }
-    return DSC_OK;
+    return dsc_leave_stream(ctx, st);
 }
 
 extern "C" int dsc_gather_cells(dsc_ctx *ctx, const float *grid, const int32_t *cells, int64_t n_cells, int mem,
@@ -633,6 +637,7 @@ extern "C" int dsc_gather_cells(dsc_ctx *ctx, const float *grid, const int32_t *
     const int R = ctx->tab_R, S = ctx->tab_S;
     const bool host = mem == DSC_MEM_HOST;
     cudaStream_t st = host ? ctx->s_k : (cudaStream_t)stream;
+    if ((rc = dsc_enter_stream(ctx, st))) return rc;
     size_t o = 0;
     const size_t o_grid = o;   o = align_up(o + (host ? (size_t)R * S * 4 : 0), 256);
     const size_t o_cells = o;  o = align_up(o + (host ? (size_t)n_cells * 8 : 0), 256);
@@ -652,6 +657,7 @@ extern "C" int dsc_gather_cells(dsc_ctx *ctx, const float *grid, const int32_t *
     if (host) {
         DSC_CUDA(ctx, cudaMemcpyAsync(pts_out, d_pts, (size_t)n_cells * 24, cudaMemcpyDeviceToHost, st));
         DSC_CUDA(ctx, cudaStreamSynchronize(st));
+        return DSC_OK;
     }
-    return DSC_OK;
+    return dsc_leave_stream(ctx, st);
 }

@@ -94,6 +94,24 @@ def pack_scans(scans: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray, int
     return buf, offsets, 4 * stride_cols
 
 
+def pack_scans_f64(scans: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray, int]:
+    """float64 clouds (Open3D-downsampled: np.asarray(pcd.points)) -> one packed (N_total, 3) float64 buffer,
+    offsets, stride in bytes.  A single C-contiguous (N,3|4) array is passed through without a copy."""
+    offsets = np.zeros(len(scans) + 1, np.int64)
+    if len(scans) == 0:
+        return np.zeros((0, 3), np.float64), offsets, 24
+    for s in scans:
+        if s.ndim != 2 or s.shape[1] not in (3, 4):
+            raise ValueError("points must be (N,3) or (N,4)")
+    np.cumsum([s.shape[0] for s in scans], out=offsets[1:])
+    if len(scans) == 1 and scans[0].dtype == np.float64 and scans[0].flags.c_contiguous and scans[0].shape[0]:
+        return scans[0], offsets, 8 * scans[0].shape[1]
+    buf = np.empty((int(offsets[-1]), 3), np.float64)
+    for s, a, b in zip(scans, offsets[:-1], offsets[1:]):
+        buf[a:b] = s[:, :3]
+    return buf, offsets, 24
+
+
 class Engine:
     """Owns one dsc_ctx (one GPU).  Not thread-safe; must not be used from forked children."""
 
@@ -212,6 +230,60 @@ class Engine:
     def build_scans(self, scans: Sequence[np.ndarray], params: ScanContextParams, want_norm=False):
         pts, offsets, stride = pack_scans(scans)
         return self.build_host(pts, offsets, params, stride_bytes=stride, want_norm=want_norm)
+
+    # -- K1, float64 clouds --------------------------------------------------------------------
+    def build_host_f64(self, pts: np.ndarray, offsets: np.ndarray, params: ScanContextParams,
+                       stride_bytes: Optional[int] = None, want_stats: bool = True):
+        """float64 points (what Open3D's voxel_down_sample returns; scan_context_node.py:93-100,161-168,
+        scaner_version2.py:126-133): the polar chain runs in float64.  Returns (grids, stats|None); the grids
+        are float64 for variant A (float64 heights) and float32 for variant B (heights cast before the max)."""
+        pts = np.asarray(pts)
+        if pts.dtype != np.float64 or not pts.flags.c_contiguous:
+            raise TypeError("pts must be a C-contiguous float64 array")
+        if stride_bytes is None:
+            stride_bytes = 8 * pts.shape[1]
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        out = np.empty((n, params.num_ring, params.num_sector),
+                       np.float64 if params.variant == _ffi.VARIANT_A else np.float32)
+        stats = np.zeros((n, len(_ffi.STATS_FIELDS)), np.int64) if want_stats else None
+        cp = params.c()
+        self._check(self._lib.dsc_sc_build_batch_f64(self._h, C.byref(cp), float(params.height_offset), _ptr(pts),
+                                                     _ptr(offsets), n, int(stride_bytes), _ffi.MEM_HOST, _ptr(out),
+                                                     _ptr(stats), None))
+        return out, stats
+
+    def build_device_f64(self, pts, offsets: np.ndarray, params: ScanContextParams, out, stats=None,
+                         stride_bytes: int = 24, stream: Optional[int] = None):
+        """Device-resident float64 batch (torch CUDA tensors; ``out`` float64 for variant A, float32 for B)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        cp = params.c()
+        self._check(self._lib.dsc_sc_build_batch_f64(self._h, C.byref(cp), float(params.height_offset), _ptr(pts),
+                                                     _ptr(offsets), offsets.size - 1, int(stride_bytes),
+                                                     _ffi.MEM_DEVICE, _ptr(out), _ptr(stats), C.c_void_p(stream)))
+
+    def build_scans_f64(self, scans: Sequence[np.ndarray], params: ScanContextParams):
+        pts, offsets, stride = pack_scans_f64([np.asarray(s) for s in scans])
+        return self.build_host_f64(pts, offsets, params, stride_bytes=stride)
+
+    def build_any(self, points: np.ndarray, params: ScanContextParams):
+        """One cloud of either dtype -> (grid, stats row), binned in the dtype NumPy would use: float32 clouds in
+        float32 (K1), everything else (float64, integer, float16 ...) promoted to float64 as NumPy's
+        x*x, sqrt and arctan2 would.  Variant A grids come back as float64 either way, like the reference's."""
+        pts = np.asarray(points)
+        if pts.dtype == np.float32:
+            grids, _, stats = self.build_scans([pts], params)
+            g = grids[0].astype(np.float64) if params.variant == _ffi.VARIANT_A else grids[0]
+            return g, stats[0]
+        if pts.dtype != np.float64:
+            if pts.dtype == np.float16 or not np.can_cast(pts.dtype, np.float64, "safe"):
+                raise TypeError(f"cannot bin points of dtype {pts.dtype}")
+            pts = pts.astype(np.float64)
+        grids, stats = self.build_scans_f64([pts], params)
+        return grids[0], stats[0]
 
     # -- K4 ------------------------------------------------------------------------------------
     def normalize01_host(self, grids: np.ndarray) -> np.ndarray:

@@ -10,8 +10,8 @@ patched in (``distropointclouds_b200.compat.install()``):
 * :class:`ScanContextComputer`  -- scan_context_node.py:24-188 (live generator, variant B).
 
 GUI / plotting members of the reference (Open3D windows, matplotlib PNGs) are out of scope and
-not mirrored.  Voxel down-sampling (Open3D, un-vendored, parity unpinned) is not performed:
-callers pass the points they want binned.
+not mirrored.  float32 clouds (the .bin dtype) are binned in float32, float64 clouds (what Open3D's
+voxel_down_sample returns) in float64, exactly as NumPy promotes the reference's expressions.
 """
 from __future__ import annotations
 
@@ -87,8 +87,9 @@ class ScanContext:
 
     # -- scaner_version2.py:64-115 ---------------------------------------------------------------
     def ptcloud2sc_vectorized(self, ptcloud, num_sector, num_ring, max_length):
-        """(N,3) float32 points -> (num_ring, num_sector) float64 grid (float32-representable
-        values; callers cast to float32 on save), empty cells 0."""
+        """(N,3) points -> (num_ring, num_sector) float64 grid, empty cells 0.  float32 points (the .bin dtype)
+        give float32-representable values; float64 points (use_downsampling=1, :126-133) are binned in float64
+        and keep their float64 heights.  Callers cast to float32 on save."""
         cls = type(self) if isinstance(self, ScanContext) else ScanContext
         params = ScanContextParams(
             num_ring=int(num_ring), num_sector=int(num_sector), max_length=float(max_length),
@@ -98,15 +99,11 @@ class ScanContext:
             # Python ints make them weak scalars -> float32 `//`   (scaner_version2.py:70-71,93-94)
             gap_f32=not (_is_np_int(num_ring) or _is_np_int(num_sector) or isinstance(max_length, np.floating)),
         )
-        pts = np.asarray(ptcloud)
-        if pts.dtype != np.float32:
-            raise TypeError("the engine bins float32 points (the .bin dtype); float64 input "
-                            "(Open3D-downsampled clouds) is not supported yet")
-        grids, _, stats = cls._engine().build_scans([pts], params)
-        ScanContext.last_stats = dict(zip(_STATS, (int(v) for v in stats[0])))
+        grid, stats = cls._engine().build_any(ptcloud, params)
+        ScanContext.last_stats = dict(zip(_STATS, (int(v) for v in stats)))
         if cls.strict:
-            _raise_like_reference(stats[0])
-        return grids[0].astype(np.float64)
+            _raise_like_reference(stats)
+        return grid
 
     # -- scaner_version2.py:117-178 / kitti_dataset.py:100-127 ------------------------------------
     def genSCs(self):
@@ -172,14 +169,11 @@ class ScanContextComputer:
         pts = np.asarray(pts_xyz)
         if pts.size == 0:                                   # :107-108
             return np.zeros((self.ring_res, self.sector_res), dtype=np.float32)
-        if pts.dtype != np.float32:
-            raise TypeError("the engine bins float32 points; float64 input (Open3D-downsampled clouds) "
-                            "is not supported yet")
         params = ScanContextParams(int(self.ring_res), int(self.sector_res), float(self.max_length),
                                    _ffi.VARIANT_B, self.use_full_height_range, self.custom_height_offset)
-        grids, _, stats = default_engine(self.device).build_scans([pts], params)
-        self.last_stats = dict(zip(_STATS, (int(v) for v in stats[0])))
-        return grids[0]
+        grid, stats = default_engine(self.device).build_any(pts, params)      # float32 or float64 cloud
+        self.last_stats = dict(zip(_STATS, (int(v) for v in stats)))
+        return grid
 
     # -- scan_context_node.py:159-188 (numeric part: grid + .npy; the PNG render is out of scope) --
     def compute_and_save(self, pts_xyz: np.ndarray, stamp_stem: str):

@@ -16,7 +16,9 @@
  *   - `mem` says where the *data* pointers of that call live: DSC_MEM_HOST or DSC_MEM_DEVICE.
  *     Small control arrays (offsets, params, tables) are always host pointers.
  *   - `stream` is a cudaStream_t (as void*).  With DSC_MEM_DEVICE the call is stream-ordered and
- *     asynchronous; with DSC_MEM_HOST the call returns after the results are in the host buffers.
+ *     asynchronous (consecutive calls on one context are ordered after one another even when they use
+ *     different streams: the context's scratch is shared); with DSC_MEM_HOST the call returns after the
+ *     results are in the host buffers.
  *   - Bad points are data, not errors: they are dropped and counted in dsc_scan_stats; the
  *     Python shim raises IndexError (as the reference does) when strict mode is on.
  *   - A context belongs to one device and is not thread-safe.  There is no CPU fallback: without
@@ -77,6 +79,9 @@ typedef struct {
     int64_t n_clamped_ring;    /* A: r beyond max_length, clamped into ring num_ring-1 (:93) */
     int64_t n_out_of_range;    /* B: r > max_length, dropped (:134-137) */
     int64_t n_slow_path;       /* points that failed the fast-path screen and took the fdlibm path */
+    int64_t n_boundary;        /* float64 input only: points whose sector coordinate theta/gap_sector lies within
+                                  num_sector * 2^-50 of an integer -- the only points on which two faithful float64
+                                  arctan2 implementations (NumPy-SVML, glibc, fdlibm) can pick different sectors */
 } dsc_scan_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -89,15 +94,13 @@ const char *dsc_last_error(const dsc_ctx *ctx);
 int dsc_set_timing(dsc_ctx *ctx, int enabled);
 float dsc_last_kernel_ms(const dsc_ctx *ctx);
 /* Engine options (debugging / A-B measurements; defaults are the measured best, see profiles/r1_notes.md):
- *   "k1_impl"        0 = auto (k1_scan; generic fallback for 12-byte stride / odd shapes), 1 = chunked L2-key
- *                    kernels, 2 = CTA-pair half-grid kernel, 3 = k1_scan only, 4 = tile-scheduler kernel
+ *   "k1_impl"        0 = auto (k1_scan; generic kernels for 12-byte stride / odd shapes / few small scans),
+ *                    1 = generic L2-key kernels only, 3 = k1_scan whenever the shape allows
  *   "sc_cfg"         k1_scan launch shape: 0 = 768 threads x 3 loads, 1 = 1024 x 3, 2 = 1024 x 2
  *   "sc_smem_rows"   resident ring rows of k1_scan (-1 = as many as the carve-out allows)
  *   "sc_split"       -1 = auto, 0 = never cut scans into work items, 1 = always
  *   "sc_item_points" target points per work item when scans are cut (default 131072)
- *   "sc_loader"      0 = 128-bit register loads, 1 = TMA ring (cp.async.bulk + mbarrier)
- *   "l2_persist"     1 = keep the private key slots in the persisting part of L2 during the launch
- *   "st_cfg", "st_slots", "hg_cfg", "pf_dist", "no_defgrid"   knobs of the A/B kernels */
+ *   "no_defgrid"     1 = do not use the default-grid specialisation of k1_scan */
 int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value);
 /* Number of engine kernels launched since the context was created. */
 int64_t dsc_kernel_launches(const dsc_ctx *ctx);
@@ -122,6 +125,21 @@ int dsc_host_free(dsc_ctx *ctx, void *p);
 int dsc_sc_build_batch(dsc_ctx *ctx, const dsc_params *params, const void *pts,
                        const int64_t *offsets, int n_scans, int pts_stride_bytes, int mem,
                        float *out_grids, float *out_norm, dsc_scan_stats *stats, void *stream);
+
+/* ---- K1, float64 points ------------------------------------------------------------------------
+ * The same two methods when the cloud is float64 -- what Open3D's voxel_down_sample returns, i.e. the live node's
+ * only call path (scan_context_node.py:93-100 -> :161-168 -> _scan_context, variant B) and the offline generator
+ * with use_downsampling=1 (scaner_version2.py:126-133 -> ptcloud2sc_vectorized, variant A).  NumPy then runs the
+ * polar chain in float64; float64 arctan2 is the fdlibm algorithm (see dsc_scan_stats.n_boundary).
+ *   pts              float64 rows x,y,z; row i starts at byte i*pts_stride_bytes (24, or 32 for padded rows)
+ *   height_offset    custom_height_offset as float64 (the add is a float64 add; params->height_offset is ignored)
+ *   out_grids        variant A: float64 [n_scans][num_ring][num_sector] (float64 heights, scaner_version2.py:97-108)
+ *                    variant B: float32 [n_scans][num_ring][num_sector] (heights cast to float32 before the
+ *                    reduction, scan_context_node.py:150-151)
+ *   params->flags    ignored (there is no screened path and no float32 `//` for float64 input) */
+int dsc_sc_build_batch_f64(dsc_ctx *ctx, const dsc_params *params, double height_offset, const void *pts,
+                           const int64_t *offsets, int n_scans, int pts_stride_bytes, int mem,
+                           void *out_grids, dsc_scan_stats *stats, void *stream);
 
 /* ---- K4: per-grid min/max -> [0,1]  (to_tensor01, tiny_sc_ped.py:54-60;
  *      scaner_version2.py:402-407; scan_context_node.py:171-173) ------------------------------ */

@@ -41,6 +41,16 @@ int orc_sc_build_batch(const orc_params *p, const float *pts, const int64_t *off
                        int stride_floats, float *out, orc_stats *st, int n_threads);
 int orc_max_threads(void);
 
+/* float64 point clouds (dsc_oracle_f64.c): fdlibm double atan2; variant A -> float64 grid, variant B -> float32 grid */
+double orc_atan(double x);
+double orc_atan2(double y, double x);
+void   orc_atan2_array(const double *y, const double *x, double *out, int64_t n);
+int orc_point_bin_f64(const orc_params *p, double height_offset, double x, double y, double z,
+                      double theta_rad_override, int use_override, int *ring, int *sector, double *zval,
+                      int *boundary);
+int orc_sc_build_f64(const orc_params *p, double height_offset, const double *pts, int64_t n, int stride_doubles,
+                     const double *theta_override, double *out64, float *out32, orc_stats *st, int64_t *n_boundary);
+
 void orc_normalize01(const float *grid, int64_t cells, float *out, float *mn_out, float *mx_out);
 
 int64_t orc_raster_box(int R, int S, const double *r_centers, const double *cos_tab,

@@ -56,8 +56,8 @@ class OrcStats(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (``make -C oracle``)."""
-    src = os.path.join(_HERE, "dsc_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("dsc_oracle.c", "dsc_oracle_f64.c", "dsc_oracle.h", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -85,6 +85,13 @@ def lib():
                                          C.POINTER(OrcStats), C.c_int]
         L.orc_sc_build_batch.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
+        L.orc_atan2.argtypes = [C.c_double, C.c_double]
+        L.orc_atan2.restype = C.c_double
+        L.orc_atan2_array.argtypes = [dp, dp, dp, C.c_int64]
+        L.orc_atan2_array.restype = None
+        L.orc_sc_build_f64.argtypes = [C.POINTER(OrcParams), C.c_double, dp, C.c_int64, C.c_int, dp, dp, fp,
+                                       C.POINTER(OrcStats), lp]
+        L.orc_sc_build_f64.restype = C.c_int
         L.orc_normalize01.argtypes = [fp, C.c_int64, fp, fp, fp]
         L.orc_normalize01.restype = None
         L.orc_raster_box.argtypes = [C.c_int, C.c_int, dp, dp, dp] + [C.c_double] * 6 + [ip, C.c_int64]
@@ -122,6 +129,43 @@ def atan2f(y, x) -> np.ndarray:
     out = np.empty_like(y)
     lib().orc_atan2f_array(_p(y, C.c_float), _p(x, C.c_float), _p(out, C.c_float), y.size)
     return out
+
+
+def atan2(y, x) -> np.ndarray:
+    """float64 arctan2, fdlibm flavour (dsc_oracle_f64.c)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(y)
+    lib().orc_atan2_array(_p(y, C.c_double), _p(x, C.c_double), _p(out, C.c_double), y.size)
+    return out
+
+
+def sc_build_f64(points: np.ndarray, params: Params = Params(), theta_override=None):
+    """One float64 scan (what Open3D's voxel_down_sample hands the reference) -> (grid, stats dict).
+    Variant A returns a float64 grid (scaner_version2.py:97-108), variant B a float32 grid
+    (scan_context_node.py:150-151).  stats has the extra key ``n_boundary``."""
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[1] < 3:
+        raise ValueError("points must be (N,>=3)")
+    n = pts.shape[0]
+    is_a = params.variant == VARIANT_A
+    out = np.empty((params.num_ring, params.num_sector), dtype=np.float64 if is_a else np.float32)
+    st = OrcStats()
+    nb = C.c_int64(0)
+    th = None
+    if theta_override is not None:
+        th = np.ascontiguousarray(theta_override, dtype=np.float64)
+        assert th.size == n
+    cp = params.c()
+    rc = lib().orc_sc_build_f64(C.byref(cp), float(params.height_offset), _p(pts, C.c_double), n, pts.shape[1],
+                                _p(th, C.c_double) if th is not None else None,
+                                _p(out, C.c_double) if is_a else None, _p(out, C.c_float) if not is_a else None,
+                                C.byref(st), C.byref(nb))
+    if rc:
+        raise ValueError(f"orc_sc_build_f64 rc={rc}")
+    d = st.as_dict()
+    d["n_boundary"] = int(nb.value)
+    return out, d
 
 
 def as_packed(points: np.ndarray):

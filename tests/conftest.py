@@ -62,13 +62,14 @@ def orc():
     return oracle
 
 
-@pytest.fixture(scope="session", params=["auto", "l2keys", "halfgrid", "scan", "scan_nosplit", "tile"])
+@pytest.fixture(scope="session", params=["auto", "l2keys", "scan", "scan_nosplit"])
 def engine(request):
-    """One engine per K1 implementation: the default (persistent scan kernel; small batches and big scans are
-    split into work items) and the A/B variants."""
+    """One engine per K1 path: the default (persistent scan kernel; small batches and big scans are split into
+    work items), the generic L2-key kernels, the scan kernel forced on every shape it takes, and the scan kernel
+    with whole-scan items only (spill lists + band passes even for one tiny scan)."""
     from distropointclouds_b200.engine import Engine
     e = Engine(0)
-    e.set_option("k1_impl", {"auto": 0, "l2keys": 1, "halfgrid": 2, "scan": 3, "scan_nosplit": 3, "tile": 4}[request.param])
+    e.set_option("k1_impl", {"auto": 0, "l2keys": 1, "scan": 3, "scan_nosplit": 3}[request.param])
     if request.param == "scan_nosplit":
         e.set_option("sc_split", 0)          # one CTA per scan even for tiny batches
     yield e

@@ -59,3 +59,25 @@ long long hm_defgrid_mismatches(double max_length, const float *xyz, long long n
 unsigned hm_float_to_key(float z) { return dsc::float_to_key(z); }
 float hm_key_to_float(unsigned k) { return dsc::key_to_float(k); }
 }
+
+// ---- float64 clouds (dsc_math_f64.cuh) -----------------------------------------------------------------------
+#include "../distropointclouds_b200/csrc/dsc_math_f64.cuh"
+extern "C" {
+double hm_atan2(double y, double x) { return dsc::atan2_fdlibm(y, x); }
+void hm_atan2_array(const double *y, const double *x, double *out, long long n)
+{
+    for (long long i = 0; i < n; ++i) out[i] = dsc::atan2_fdlibm(y[i], x[i]);
+}
+void hm_bin64(int R, int S, double max_length, int variant, int full_height, double offset, const double *xyz,
+              long long n, int stride_doubles, int *cell, int *status, int *boundary, double *z)
+{
+    const dsc::Bin64Cfg c = dsc::make_bin64_cfg(R, S, max_length, variant, full_height, offset);
+    for (long long i = 0; i < n; ++i) {
+        const double *p = xyz + i * stride_doubles;
+        const dsc::Bin64Result b = variant == 0 ? dsc::bin64_a(c, p[0], p[1], p[2]) : dsc::bin64_b(c, p[0], p[1], p[2]);
+        cell[i] = b.cell; status[i] = b.status; boundary[i] = b.boundary; z[i] = b.z;
+    }
+}
+unsigned long long hm_double_to_key(double z) { return dsc::double_to_key(z); }
+double hm_key_to_double(unsigned long long k) { return dsc::key_to_double(k); }
+}

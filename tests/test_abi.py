@@ -37,7 +37,7 @@ def test_version_string(lib):
 def test_struct_layouts_match_header():
     from distropointclouds_b200 import _ffi
     assert C.sizeof(_ffi.DscParams) == 32
-    assert C.sizeof(_ffi.DscScanStats) == 48
+    assert C.sizeof(_ffi.DscScanStats) == 56
     assert _ffi.DscParams.max_length.offset == 8 and _ffi.DscParams.flags.offset == 28
 
 

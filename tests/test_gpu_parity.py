@@ -167,7 +167,7 @@ def test_device_path_equals_host_path(engine, orc):
     d_pts = torch.from_numpy(np.concatenate([np.zeros((pad, 4), np.float32), pts])).cuda()
     out = torch.empty((5, 160, 720), dtype=torch.float32, device="cuda")
     nrm = torch.empty_like(out)
-    st = torch.zeros((5, 6), dtype=torch.int64, device="cuda")
+    st = torch.zeros((5, 7), dtype=torch.int64, device="cuda")
     engine.build_device(d_pts, offs + pad, p, out, nrm, st)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), host) and np.array_equal(nrm.cpu().numpy(), norm_h)
@@ -423,7 +423,7 @@ def test_full_size_batch_properties(orc):
     e = Engine(0)
     try:
         out = torch.empty((B, 160, 720), dtype=torch.float32, device="cuda")
-        st = torch.zeros((B, 6), dtype=torch.int64, device="cuda")
+        st = torch.zeros((B, 7), dtype=torch.int64, device="cuda")
         e.build_device(pts, offs, P(), out, None, st)
         again = torch.empty_like(out)
         e.build_device(pts, offs, P(), again, None, None)
@@ -440,3 +440,49 @@ def test_full_size_batch_properties(orc):
             assert torch.equal(small, out[a:a + 64]), a
     finally:
         e.close()
+
+
+def test_full_size_screened_equals_exact_only():
+    """The screened fast path against DSC_FLAG_EXACT_ONLY on every one of the 4096 x 120 000 = 491 M points of
+    BASELINE configs[2] (real MUFU.RCP / MUFU.SQRT, not the host emulation): all 4096 grids and every counter but
+    n_slow_path must be identical -- the screen's error budget (dsc_math.cuh) checked at device scale."""
+    import torch
+    from distropointclouds_b200.engine import Engine
+    from distropointclouds_b200.synth import synth_batch_device
+    B, N = 4096, 120000
+    pts = synth_batch_device(B, N, 64, seed=5, device="cuda")
+    N = pts.shape[1]
+    offs = np.arange(B + 1, dtype=np.int64) * N
+    e = Engine(0)
+    try:
+        for variant, ml, full in ((0, 20.0, True), (1, 80.0, False)):
+            fast = torch.empty((B, 160, 720), dtype=torch.float32, device="cuda")
+            exact = torch.empty_like(fast)
+            st_f = torch.zeros((B, 7), dtype=torch.int64, device="cuda")
+            st_e = torch.zeros_like(st_f)
+            e.build_device(pts, offs, P(max_length=ml, variant=variant, full_height=full), fast, None, st_f)
+            e.build_device(pts, offs, P(max_length=ml, variant=variant, full_height=full, exact_only=True), exact, None, st_e)
+            torch.cuda.synchronize()
+            assert torch.equal(fast, exact), variant
+            assert torch.equal(st_f[:, :5], st_e[:, :5]), variant
+            assert int(st_f[:, 5].sum()) > 0 and int(st_e[:, 5].sum()) == 0
+            del fast, exact
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("n_scans", [70, 150, 300])
+def test_many_small_scans_with_empty_ones(engine, orc, n_scans):
+    """Batches of 65+ small scans with empty scans among them (an empty scan has no tile and no work item; round 1's
+    tile scheduler could wait for one forever -- ADVICE r1)."""
+    rng = np.random.default_rng(n_scans)
+    scans = []
+    for i in range(n_scans):
+        n = 0 if i < 4 or i % 37 == 0 else int(rng.integers(3000, 7000))
+        p = (rng.standard_normal((n, 4)) * [9, 9, 1.5, 1]).astype(np.float32)
+        scans.append(p)
+    got, _, stats = engine.build_scans(scans, P())
+    for i, sc in enumerate(scans):
+        ref = orc.sc_build(sc)[0] if len(sc) else np.zeros((160, 720), np.float32)
+        assert np.array_equal(got[i], ref), i
+        assert int(stats[i][0]) == len(sc)

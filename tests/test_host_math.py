@@ -17,8 +17,8 @@ def hm():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostmath.so")
     src = os.path.join(ROOT, "tests", "host_math.cpp")
-    hdr = os.path.join(ROOT, "distropointclouds_b200", "csrc", "dsc_math.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "distropointclouds_b200", "csrc", h) for h in ("dsc_math.cuh", "dsc_math_f64.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-msse2",
                                "-DDSC_HAVE_FAST", "-o", so, src])
     L = C.CDLL(so)
