@@ -206,7 +206,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     eng = Engine(local_rank)
-    for name in ("k1_impl", "sc_cfg", "no_defgrid", "sc_smem_rows", "sc_split", "sc_item_points"):
+    for name in ("k1_impl", "sc_cfg", "no_defgrid", "sc_smem_rows", "sc_split", "sc_item_points", "sc_window"):
         v = getattr(args, name)
         if v is not None:
             eng.set_option(name, v)
@@ -397,7 +397,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     # A/B knobs of the engine (see dsc_api.cu); None = engine default
-    for name in ("k1-impl", "sc-cfg", "no-defgrid", "sc-smem-rows", "sc-split", "sc-item-points"):
+    for name in ("k1-impl", "sc-cfg", "no-defgrid", "sc-smem-rows", "sc-split", "sc-item-points", "sc-window"):
         ap.add_argument("--" + name, type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -40,6 +40,8 @@ struct dsc_ctx {
     size_t keys_bytes = 0;
     void *spill = nullptr;           // scan kernel: per-CTA spill lists of (cell, key) pairs
     size_t spill_bytes = 0;
+    void *probe = nullptr;           // scan kernel: ring histogram of k1_probe + the resident window's first ring
+    int sc_window = -1;              // -1: k1_probe picks the window; >= 0: fixed first ring (A/B runs)
     void *keys64 = nullptr;          // float64-input path: [slots][cells] 64-bit (variant A) or 32-bit (variant B) keys
     size_t keys64_bytes = 0;
     struct OffSlot {                 // offsets of a device-mode call: pinned staging + device copy + "consumed" event

@@ -140,7 +140,9 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         const int64_t n = h_offsets[s + 1] - h_offsets[s];
         split_items += n > item_pts ? (n + item_pts - 1) / item_pts : 1;
     }
-    const bool sc_shape_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1;
+    // (k1_scan addresses the stream with 32-bit row indices)
+    const bool sc_shape_ok = vec16 && (p->num_sector % 4) == 0 && (((uintptr_t)out) & 15) == 0 && ctx->k1_impl != 1 &&
+                             h_offsets[n_scans] < 0xffff0000LL;
     const bool want_split = ctx->sc_split == 1 ||
                             (ctx->sc_split < 0 && (n_scans < 2 * ctx->sm_count || max_pts > 3 * ctx->sc_item_points) &&
                              split_items > n_scans);
@@ -210,17 +212,31 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             // is used -- the points outside the resident rings, ~15 % on KITTI-like scans -- is ever touched)
             spill_cap = (size_t)((max_pts + nthreads - 1) / nthreads) * (size_t)nthreads;
             if (spill_cap < (size_t)nthreads) spill_cap = (size_t)nthreads;
-            const size_t need = (size_t)ctas * spill_cap * sizeof(uint2);
+            const size_t need = SC_SLOT ? (size_t)ctx->sm_count * cells * 4 : (size_t)ctas * spill_cap * sizeof(uint2);
             if (need > ctx->spill_bytes) {
                 if (ctx->spill) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->spill); }
                 ctx->spill = nullptr;
                 ctx->spill_bytes = 0;
                 DSC_CUDA(ctx, cudaMalloc(&ctx->spill, need));
                 ctx->spill_bytes = need;
+                if (SC_SLOT) DSC_CUDA(ctx, cudaMemsetAsync(ctx->spill, 0, need, st));     // key slots: left zeroed by the kernel
             }
         }
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
         DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, sync_bytes, st));
+        // resident window: ring histogram of sampled points -> first ring r0 (device-side; no host round trip)
+        if (!ctx->probe) DSC_CUDA(ctx, cudaMalloc(&ctx->probe, (PROBE_MAXR + 4) * sizeof(unsigned int)));
+        unsigned int *probe = (unsigned int *)ctx->probe;
+        int *window = (int *)(probe + PROBE_MAXR + 2);
+        DSC_CUDA(ctx, cudaMemsetAsync(probe, 0, (PROBE_MAXR + 4) * sizeof(unsigned int), st));
+        if (total_pts > 0 && p->num_ring <= PROBE_MAXR && ns < p->num_ring && ctx->sc_window < 0) {
+            k1_probe<<<PROBE_BLOCKS, PROBE_THREADS, 0, st>>>(pts, h_offsets[0], total_pts, (float)(p->num_ring / p->max_length),
+                                                             p->num_ring, ns - 1, probe, window);
+            if ((rc = dsc_check_launch(ctx, "k1_probe"))) return rc;
+        } else if (ctx->sc_window > 0) {                 // A/B override
+            const int w = ctx->sc_window <= p->num_ring - ns ? ctx->sc_window : (p->num_ring - ns > 0 ? p->num_ring - ns : 0);
+            DSC_CUDA(ctx, cudaMemcpyAsync(window, &w, sizeof(int), cudaMemcpyHostToDevice, st));
+        }
         unsigned long long *stp = (unsigned long long *)stats;
         const bool full = p->full_height != 0;
         const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
@@ -229,7 +245,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP>,                                      \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
         k1_scan<F, V, H, U, NT, D, SP><<<ctas, NT, sc_smem, st>>>(pts, d_offsets, n_scans, (uint2 *)ctx->spill, \
-                                                                  spill_cap, out, stp, cursor, ns, cfg, spa);   \
+                                                                  spill_cap, out, stp, cursor, ns, window, cfg, \
+                                                                  spa);                                         \
     } while (0)
 #define SC_LAUNCH3(F, V, H, U, NT, D)                                                                           \
     do {                                                                                                        \
@@ -359,6 +376,8 @@ void dsc_k1_release(dsc_ctx *ctx)
     free_stage(ctx);
     if (ctx->keys) cudaFree(ctx->keys);
     if (ctx->spill) cudaFree(ctx->spill);
+    if (ctx->probe) cudaFree(ctx->probe);
+    ctx->probe = nullptr;
     for (int i = 0; i < DSC_OFF_RING; ++i) {
         if (ctx->off[i].d) cudaFree(ctx->off[i].d);
         if (ctx->off[i].h) cudaFreeHost(ctx->off[i].h);

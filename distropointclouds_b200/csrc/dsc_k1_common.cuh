@@ -90,9 +90,10 @@ __device__ __forceinline__ void fill_exact_args(ExactArgs *ea, const BinCfg &cfg
 // items) or go to the scan's key grid with RED.MAX (split items).
 struct SmemRows {
     uint32_t base;   // shared-window address of the resident rows
-    int lim;         // cells below lim are resident rows 0 .. ns-2            (0 when nothing is resident)
-    int last;        // first cell of the clamp ring, kept in resident row ns-1 (INT_MAX when nothing is)
-    int shift;       // lim - last: clamp-ring cell -> resident row ns-1 (sc_update only)
+    int c0;          // first cell of the resident window (ring r0)
+    int lim;         // cells c0 .. c0+lim-1 are resident rows 0 .. ns-2
+    int last;        // first cell of the clamp ring, kept in resident row ns-1
+    int shift;       // lim - last: clamp-ring cell -> resident row ns-1
 };
 
 // tile -> (scan, tile in scan)

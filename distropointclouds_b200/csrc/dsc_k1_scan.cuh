@@ -5,16 +5,19 @@
 // ---- K1 main path: persistent CTAs, one work item (a scan, or a slice of a big scan) at a time ------------------
 // A CTA streams the item's points once (128-bit loads, two register sets ping-pong), bins each point once and
 // folds it into the key grid.  The 460 KB grid does not fit one SM, so the reduction runs in ring bands:
-//   pass 1 (the stream)  the hot ring rows -- rings 0 .. ns-2 and the clamp ring R-1, 75-90 % of the points of a
-//                        KITTI-like scan -- live in shared memory (LDS pre-check + ATOMS.MAX).  A point of any other
-//                        ring is NOT reduced yet: its (cell, key) pair is appended to the warp's private spill list
-//                        (one ballot, one coalesced 8-byte store per lane; the list is a few hundred KB per CTA and
-//                        stays in L2).
+//   pass 1 (the stream)  the hot ring rows -- a window of ns-1 rings starting at ring r0, plus the clamp ring R-1 --
+//                        live in shared memory (LDS pre-check + ATOMS.MAX).  r0 is chosen per launch by k1_probe
+//                        from a ring histogram of 64 Ki sampled points (a LiDAR sees nothing closer than ~3 m, so
+//                        rings 0..20 are empty and the dense ground rings start behind them: the best window holds
+//                        85 % of the points of the bench batch, the window at ring 0 only 70 %).  A point of any
+//                        other ring is NOT reduced yet: its (cell, key) pair is appended to the warp's private
+//                        spill list (one ballot, one coalesced 8-byte store per lane; the lists are ~100 KB per CTA
+//                        and stay in L2).
 //   write-out            the resident rows are decoded to floats (coalesced 128-bit streaming stores) and re-zeroed;
-//   pass 2 (per band)    the same shared-memory rows now stand for the next band of up to ns rings: every warp
-//                        re-reads its own spill list (L2 hits, 128-bit loads) and folds the band's entries in with
-//                        the same LDS pre-check + ATOMS.MAX; the band is decoded and written out; repeat until
-//                        ring R-2.
+//   pass 2 (per band)    the same shared-memory rows now stand for the next band of up to ns of the remaining rings:
+//                        every warp folds the band's entries of its own spill list in with the same LDS pre-check +
+//                        ATOMS.MAX (L2 hits, 128-bit loads); the band is decoded and written out; repeat until
+//                        every ring is done (two bands on the default grid).
 // So every max-reduction is a shared-memory atomic, HBM sees each point once and each output cell once, there are
 // no global atomics, no key slots to read back and re-zero, and no synchronisation between CTAs for whole-scan items.
 // (Round 1 reduced the non-resident rings with RED.MAX on a private L2 slot per CTA: 72 M scattered L2 atomics per
@@ -23,6 +26,9 @@ constexpr int SC_THREADS = 1024;
 #ifndef SC_DU
 #define SC_DU 4                       // 128-bit L2 loads in flight per thread in the split-mode decode
 #endif
+#ifndef SC_SLOT
+#define SC_SLOT 0                     // 1 (A/B builds): whole-scan items reduce the non-resident rings with RED.MAX on a private
+#endif                                // L2 key slot per CTA and read it back (the round-1 form) instead of spill lists + bands
 #ifndef SC_LU
 #define SC_LU 4                       // 128-bit spill-list loads in flight per lane in pass 2
 #endif
@@ -88,9 +94,10 @@ __device__ __forceinline__ void sc_commit(const float zv, const int cell, bool v
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     valid = valid && (zv == zv);                 // NaN never wins (scaner_version2.py:107)
     if (!FULL) valid = valid && (zv > 0.0f);     // offset mode: cells start at 0, strict '>'
-    const bool res = cell < sm.lim || cell >= sm.last;
+    const bool win = (uint32_t)(cell - sm.c0) < (uint32_t)sm.lim;               // rings r0 .. r0+ns-2
+    const bool res = win || cell >= sm.last;
     if (valid && res) {
-        const int local = cell < sm.lim ? cell : cell + sm.shift;               // clamp ring -> row ns-1
+        const int local = win ? cell - sm.c0 : cell + sm.shift;                 // clamp ring -> row ns-1
         const uint32_t addr = sm.base + (uint32_t)local * 4u;
         if (key > lds_u32(addr)) reds_max_u32(addr, key);
     }
@@ -98,7 +105,9 @@ __device__ __forceinline__ void sc_commit(const float zv, const int cell, bool v
         const unsigned m = __ballot_sync(0xffffffffu, valid && !res);
         if (m) {                                 // warp-uniform
             uint2 *w = reinterpret_cast<uint2 *>(gp);
+#ifndef SC_TIMING_NO_SPILL                       // (timing experiments only: wrong grids)
             if (valid && !res) st_spill(w + __popc(m & lanemask_lt()), (uint32_t)cell, key);
+#endif
             gp = reinterpret_cast<uint32_t *>(w + __popc(m));
         }
     } else {
@@ -141,11 +150,13 @@ __device__ __forceinline__ void sc_exact_batch(const uint32_t queue, const unsig
 }
 
 // One point per lane, called warp-uniformly (`active` masks lanes past the end of the item).
+// (`qoff`: byte offset of the exact-path queues from the rows; the warp's own queue address is only formed on the rare path)
 template <int VARIANT, bool FULL, bool DEF, bool SPILL>
 __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v, const bool active,
-                                         uint32_t *&gp, unsigned &n_clamped, unsigned long long *__restrict__ st,
-                                         const SmemRows sm, const uint32_t queue, unsigned &qcount)
+                                         uint32_t *&gp, unsigned &n_clamped, unsigned long long *__restrict__ stats,
+                                         const int scan, const SmemRows sm, const uint32_t qoff, unsigned &qcount)
 {
+    unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
     int ring, sector;
     bool beyond;
     bool ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
@@ -162,6 +173,7 @@ __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea,
     const unsigned m = __ballot_sync(0xffffffffu, active && !ok);
     if (m) {                                     // warp-uniform, rare
         const unsigned lane = threadIdx.x & 31u;
+        const uint32_t queue = sm.base + qoff + (threadIdx.x >> 5) * SCQ_WARP_BYTES;
         if (active && !ok) {
             const uint32_t a = queue + (qcount + __popc(m & ((1u << lane) - 1u))) * 4u;
             sts_f32(a, v.x);
@@ -179,8 +191,10 @@ __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea,
 // exact-only flavour (DSC_FLAG_EXACT_ONLY, non-dyadic gaps): every point takes the fdlibm chain
 template <int VARIANT, bool FULL, bool SPILL>
 __device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4 v, const bool active, uint32_t *&gp,
-                                               unsigned &n_clamped, unsigned long long *__restrict__ st, const SmemRows sm)
+                                               unsigned &n_clamped, unsigned long long *__restrict__ stats, const int scan,
+                                               const SmemRows sm)
 {
+    unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
     uint2 b = make_uint2((uint32_t)dsc::PT_NONFINITE << 27, 0u);
     if (active) {
         b = hg_bin_exact<VARIANT, FULL>(v.x, v.y, v.z, ea);
@@ -200,10 +214,11 @@ __device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4
 // end of item: the queue's remaining entries (fewer than 32)
 template <int VARIANT, bool FULL, bool SPILL>
 __device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *&gp, unsigned &n_clamped,
-                                         unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t queue,
+                                         unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t qoff,
                                          unsigned &qcount)
 {
     if (qcount) {                                // warp-uniform
+        const uint32_t queue = sm.base + qoff + (threadIdx.x >> 5) * SCQ_WARP_BYTES;
         sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gp, n_clamped, st, sm);
         qcount = 0;
     }
@@ -253,65 +268,111 @@ __device__ __forceinline__ void sc_flush_rows(uint32_t *__restrict__ srows, floa
     }
 }
 
+// fold one spill entry into the band that the shared-memory rows currently stand for: the band is the cell range
+// [lo1, lo1 + n1) followed by [lo2, lo2 + n2) (the remaining rings are the two intervals either side of the window)
+__device__ __forceinline__ void sc_band_entry(const uint32_t cell, const uint32_t key, const uint32_t sbase,
+                                              const uint32_t lo1, const uint32_t n1, const uint32_t lo2, const uint32_t n2)
+{
+    uint32_t l = cell - lo1;
+    if (l >= n1) {
+        l = cell - lo2;
+        if (l >= n2) return;
+        l += n1;
+    }
+    const uint32_t a = sbase + l * 4u;
+    if (key > lds_u32(a)) reds_max_u32(a, key);
+}
+
 // End of a whole-scan item (this CTA owns the scan): write out the resident rows, then reduce and write out the other
-// rings band by band from the spill lists.  `wseg`/`wend`: this warp's list.  Ends with a CTA barrier.
+// rings band by band from the spill lists.  `wseg`: this warp's list of `len` entries.  Ends with a CTA barrier.
 template <int NT>
 __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, const uint32_t sbase,
-                                               float *__restrict__ out_scan, const int ns, const int R, const int S,
-                                               const uint2 *__restrict__ wseg, const uint2 *__restrict__ wend)
+                                               float *__restrict__ out_scan, const int ns, const int r0, const int R,
+                                               const int S, const uint2 *__restrict__ wseg, const int len)
 {
     const int rowvec = S >> 2;
     float4 *oq = reinterpret_cast<float4 *>(out_scan);
+    const int lane2 = 2 * (int)(threadIdx.x & 31u);
     __syncthreads();                             // every shared-memory atomic and every list store of the item is done
-    // resident rows: rings 0 .. ns-2, and the clamp ring R-1 kept in row ns-1
-    sc_flush_rows<NT>(srows, oq, (ns - 1) * rowvec);
-    for (int i = threadIdx.x; i < rowvec; i += NT) {
-        uint4 *src = reinterpret_cast<uint4 *>(srows) + (ns - 1) * rowvec + i;
-        const uint4 q = *src;
-        *src = make_uint4(0, 0, 0, 0);
-        __stcs(oq + (size_t)(R - 1) * rowvec + i, sc_decode4(q));
-    }
-    const unsigned lane = threadIdx.x & 31u;
-    for (int row0 = ns - 1; row0 < R - 1; row0 += ns) {         // bands of up to ns rings
-        const int rows = R - 1 - row0 < ns ? R - 1 - row0 : ns;
-        const uint32_t c_lo = (uint32_t)row0 * (uint32_t)S, c_n = (uint32_t)rows * (uint32_t)S;
+    // resident rows: rings r0 .. r0+ns-2, and the clamp ring R-1 kept in row ns-1
+    sc_flush_rows<NT>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
+    sc_flush_rows<NT>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
+    // remaining rings, numbered v = 0 .. R-ns-1: ring v below the window, ring v + ns - 1 above it
+    const int nv = R - ns;
+    for (int b0 = 0; b0 < nv; b0 += ns) {
+        const int b1 = b0 + ns < nv ? b0 + ns : nv;
+        const int rows1 = b0 < r0 ? (b1 < r0 ? b1 : r0) - b0 : 0;               // rings b0 .. b0+rows1-1
+        const int rows2 = (b1 - b0) - rows1;                                     // rings ring2 .. ring2+rows2-1
+        const int ring2 = (b0 > r0 ? b0 : r0) + ns - 1;
+        const uint32_t lo1 = (uint32_t)b0 * (uint32_t)S, n1 = (uint32_t)rows1 * (uint32_t)S;
+        const uint32_t lo2 = (uint32_t)ring2 * (uint32_t)S, n2 = (uint32_t)rows2 * (uint32_t)S;
         __syncthreads();                         // the rows are zero again
-        // this warp's list, two entries per 128-bit load, SC_LU loads in flight per lane
-        for (const uint2 *e0 = wseg + 2u * lane; e0 < wend; e0 += 64 * SC_LU) {
+#ifndef SC_TIMING_NO_PASS2                       // (timing experiments only: wrong grids)
+        // this warp's list: two entries per 128-bit load (L2 hits), SC_LU loads in flight per lane
+        for (int i0 = lane2; i0 < len; i0 += 64 * SC_LU) {
             uint4 q[SC_LU];
 #pragma unroll
-            for (int d = 0; d < SC_LU; ++d) {
-                const uint2 *e = e0 + 64 * d;
-                if (e < wend) q[d] = ld_spill2(e);
-            }
+            for (int d = 0; d < SC_LU; ++d)
+                if (i0 + 64 * d < len) q[d] = ld_spill2(wseg + i0 + 64 * d);
 #pragma unroll
             for (int d = 0; d < SC_LU; ++d) {
-                const uint2 *e = e0 + 64 * d;
-                if (e < wend) {
-                    const uint32_t l0 = q[d].x - c_lo;
-                    if (l0 < c_n) {
-                        const uint32_t a = sbase + l0 * 4u;
-                        if (q[d].y > lds_u32(a)) reds_max_u32(a, q[d].y);
-                    }
-                    const uint32_t l1 = q[d].z - c_lo;
-                    if (e + 1 < wend && l1 < c_n) {
-                        const uint32_t a = sbase + l1 * 4u;
-                        if (q[d].w > lds_u32(a)) reds_max_u32(a, q[d].w);
-                    }
+                const int i = i0 + 64 * d;
+                if (i < len) {
+                    sc_band_entry(q[d].x, q[d].y, sbase, lo1, n1, lo2, n2);
+                    if (i + 1 < len) sc_band_entry(q[d].z, q[d].w, sbase, lo1, n1, lo2, n2);
                 }
             }
         }
+#endif
         __syncthreads();
-        sc_flush_rows<NT>(srows, oq + (size_t)row0 * rowvec, rows * rowvec);
+        sc_flush_rows<NT>(srows, oq + (size_t)b0 * rowvec, rows1 * rowvec);
+        sc_flush_rows<NT>(srows + (size_t)rows1 * S, oq + (size_t)ring2 * rowvec, rows2 * rowvec);
     }
     __syncthreads();                             // rows are zero before the next scan's atomics
+}
+
+// End of a whole-scan item, SC_SLOT form: the non-resident rings were reduced with RED.MAX on the CTA's private L2 slot
+// (a full key grid, zero == empty); decode resident rows and slot to floats and re-zero both.  Ends with a CTA barrier.
+template <int NT, int DU = 4>
+__device__ __forceinline__ void sc_finish_slot(uint32_t *__restrict__ srows, uint32_t *__restrict__ slot,
+                                               float *__restrict__ out_scan, const int ns, const int r0, const int R, const int S)
+{
+    const int rowvec = S >> 2;
+    float4 *oq = reinterpret_cast<float4 *>(out_scan);
+    __threadfence();                             // our REDs are performed ...
+    __syncthreads();                             // ... before any thread of the CTA reads the keys back
+    sc_flush_rows<NT>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
+    sc_flush_rows<NT>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
+    uint4 *kq = reinterpret_cast<uint4 *>(slot);
+    // rings 0 .. r0-1 and r0+ns-1 .. R-2, as one index range with a jump over the window
+    const int n_lo = r0 * rowvec, n_tot = (R - ns) * rowvec, jump = (ns - 1) * rowvec;
+    for (int j0 = threadIdx.x; j0 < n_tot; j0 += NT * DU) {
+        uint4 q[DU];
+#pragma unroll
+        for (int d = 0; d < DU; ++d) {
+            const int j = j0 + d * NT;
+            if (j < n_tot) q[d] = __ldcg(kq + (j < n_lo ? j : j + jump));
+        }
+#pragma unroll
+        for (int d = 0; d < DU; ++d) {
+            const int j = j0 + d * NT;
+            if (j < n_tot) {
+                const int i = j < n_lo ? j : j + jump;
+                __stcs(oq + i, sc_decode4(q[d]));
+                if (q[d].x | q[d].y | q[d].z | q[d].w) __stcg(kq + i, make_uint4(0, 0, 0, 0));
+            }
+        }
+    }
+    __threadfence();                             // the zeroes are performed ...
+    __syncthreads();                             // ... before the next scan's REDs
 }
 
 // End of a split work item: fold the resident rows into the scan's key grid (== its output grid), count the item as
 // retired, and if it was the scan's last item decode the grid in place.  Ends with a CTA barrier.
 template <int NT, int DU = 4>
-__device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid, int ns, int R,
-                                                int S, int scan, int parts, unsigned int *__restrict__ done, int *s_last)
+__device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid, int ns, int r0,
+                                                int R, int S, int scan, int parts, unsigned int *__restrict__ done,
+                                                int *s_last)
 {
     const int tid = threadIdx.x;
     const int rowvec = S >> 2;
@@ -323,7 +384,7 @@ __device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, ui
         const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
         if ((q.x | q.y | q.z | q.w) == 0u) continue;
         reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
-        uint32_t *g = grid + 4 * (size_t)(i < lim ? i : i + shift);
+        uint32_t *g = grid + 4 * (size_t)(i < lim ? i + r0 * rowvec : i + shift);
         if (q.x) red_max_global(g + 0, q.x);
         if (q.y) red_max_global(g + 1, q.y);
         if (q.z) red_max_global(g + 2, q.z);
@@ -361,18 +422,20 @@ __device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, ui
 // immediates -- was measured 10 % SLOWER than this one, which takes `ns` at run time: profiles/r1_notes.md.)
 //   spill       whole-scan items: [gridDim.x][spill_cap] (cell, key) pairs, one region per CTA, cut into per-warp lists
 //   spill_cap   entries per CTA: >= ceil(max points per scan / NT) * NT
+//   window      device int: first ring of the resident window, written by k1_probe earlier in the stream
 template <bool FAST, int VARIANT, bool FULL, int U, int NT, bool DEF, bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint2 *__restrict__ spill, const size_t spill_cap, float *__restrict__ out, unsigned long long *__restrict__ stats,
-        unsigned int *__restrict__ cursor, const int ns, const BinCfg cfg, const SplitArgs sp)
+        unsigned int *__restrict__ cursor, const int ns, const int *__restrict__ window, const BinCfg cfg,
+        const SplitArgs sp)
 {
     // NB: this kernel lives on the edge of its register budget (64 regs at 1024 threads, 80 at 768); measured
     // variants that carried more state across the streaming loop (next-item prefetch before the decode,
     // per-warp chunk counters, 8 decode loads in flight) spilled inside the loop and lost 15-40 %
     // (profiles/r1_notes.md).
     constexpr int STEP = NT * U;
-    constexpr bool SPILL = !SPLIT;
+    constexpr bool SPILL = !SPLIT && !SC_SLOT;
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ int s_next[2];
     __shared__ int s_last;
@@ -384,12 +447,14 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const uint64_t pol_stream = l2_policy_evict_first();
     // dynamic shared memory: [ns ring rows of keys][per-warp exact-path queues]
     uint32_t *const srows = smem_raw;
+    const int r0 = *window;                      // first ring of the resident window (k1_probe): 0 <= r0 <= R - ns
     SmemRows sm;
     sm.base = (uint32_t)__cvta_generic_to_shared(srows);
+    sm.c0 = r0 * S;
     sm.lim = (ns - 1) * S;                       // host guarantees ns >= 2
     sm.last = (R - 1) * S;
     sm.shift = sm.lim - sm.last;
-    const uint32_t queue = sm.base + (uint32_t)ns * (uint32_t)S * 4u + (uint32_t)(tid >> 5) * SCQ_WARP_BYTES;
+    const uint32_t qoff = (uint32_t)ns * (uint32_t)S * 4u;
     unsigned qcount = 0;
     for (int i = tid; i < ns * rowvec; i += NT) reinterpret_cast<uint4 *>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -403,73 +468,142 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     while (item < n_items) {
         // work item after this one: fetched now, consumed after the item (the round trip is hidden)
         if (tid == 0) s_next[par ^ 1] = (int)atomicAdd(cursor, 1u);
-        int scan, parts, n;
-        int64_t p0;
-        sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
         // gp: split items -- the scan's key grid (== its output grid); whole scans -- write pointer of this warp's spill list
         uint32_t *gp;
-        const uint2 *wseg = nullptr;
-        if constexpr (SPLIT) {
-            gp = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
-        } else {
-            const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;           // most points one warp can see
-            wseg = spill + (size_t)blockIdx.x * spill_cap + (size_t)(tid >> 5) * seg;
-            gp = reinterpret_cast<uint32_t *>(const_cast<uint2 *>(wseg));
-        }
-        const float4 *s4 = reinterpret_cast<const float4 *>(pts + p0 * 16);
-        unsigned n_clamped = 0;
-        unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
-        const int nfull = n / STEP;
-        const float4 *p = s4 + tid;
-        float4 a[U], b[U];
-#define SC_LD(ptr) ld_stream_f4_hint((ptr), pol_stream)
+        {   // ---- stream phase.  Nothing but the loop state may stay live here (80 registers): the item's facts
+            // (scan, first point, count) are recomputed for the finish instead of being carried through the loop.
+            int scan, parts, n;
+            int64_t p0;
+            sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
+            if constexpr (SPLIT) {
+                gp = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
+            } else if constexpr (SC_SLOT) {
+                gp = reinterpret_cast<uint32_t *>(spill) + (size_t)blockIdx.x * (size_t)cells;
+            } else {
+                const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;       // most points one warp can see
+                gp = reinterpret_cast<uint32_t *>(spill + (size_t)blockIdx.x * spill_cap + (size_t)(tid >> 5) * seg);
+            }
+            // the stream position is a 32-bit index of 16-byte rows from `pts` (host guarantees < 2^32 rows per call):
+            // one register across the loop instead of a 64-bit pointer
+            const float4 *const pts4 = reinterpret_cast<const float4 *>(pts);
+            unsigned n_clamped = 0;
+            const int nfull = n / STEP;
+            uint32_t p = (uint32_t)p0 + (uint32_t)tid;
+            float4 a[U], b[U];
+#define SC_LD(idx) ld_stream_f4_hint(pts4 + (idx), pol_stream)
 #define SC_PT(v, act)                                                                                           \
     do {                                                                                                        \
-        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, SPILL>(cfg, &s_ea, (v), (act), gp, n_clamped, st, sm, queue, qcount); \
-        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v), (act), gp, n_clamped, st, sm);                   \
+        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, SPILL>(cfg, &s_ea, (v), (act), gp, n_clamped, stats, scan, sm, qoff, qcount); \
+        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v), (act), gp, n_clamped, stats, scan, sm);          \
     } while (0)
-        if (nfull > 0) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
-        }
-        int step = 0;
-        while (step + 1 < nfull) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * NT);
-#pragma unroll
-            for (int u = 0; u < U; ++u) SC_PT(a[u], true);
-            p += 2 * STEP;
-            step += 2;
-            if (step < nfull) {
+            if (nfull > 0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
             }
+            int step = 0;
+            while (step + 1 < nfull) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) SC_PT(b[u], true);
-        }
-        if (step < nfull) {
+                for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * NT);
 #pragma unroll
-            for (int u = 0; u < U; ++u) SC_PT(a[u], true);
-        }
-        for (int i0 = nfull * STEP; i0 < n; i0 += NT) {       // ragged tail, warp-uniform trip count
-            const bool act = i0 + tid < n;
-            float4 v = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
-            if (act) v = SC_LD(s4 + i0 + tid);
-            SC_PT(v, act);
-        }
-        if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gp, n_clamped, st, sm, queue, qcount);
+                for (int u = 0; u < U; ++u) SC_PT(a[u], true);
+                p += 2 * STEP;
+                step += 2;
+                if (step < nfull) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) SC_PT(b[u], true);
+            }
+            if (step < nfull) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) SC_PT(a[u], true);
+            }
+            for (int i0 = nfull * STEP; i0 < n; i0 += NT) {       // ragged tail, warp-uniform trip count
+                const bool act = i0 + tid < n;
+                float4 v = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+                if (act) v = SC_LD((uint32_t)p0 + (uint32_t)(i0 + tid));
+                SC_PT(v, act);
+            }
+            unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
+            if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gp, n_clamped, st, sm, qoff, qcount);
 #undef SC_LD
 #undef SC_PT
-        if (stats) {
-            const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
-            if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
-            if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
+            if (stats) {
+                const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
+                if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
+                if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
+            }
         }
-        if constexpr (SPLIT)
-            sc_finish_split<NT, SC_DU>(srows, gp, ns, R, S, scan, parts, sp.done, &s_last);
-        else
-            sc_finish_scan<NT>(srows, sm.base, out + (size_t)scan * cells, ns, R, S, wseg, reinterpret_cast<const uint2 *>(gp));
+        {   // ---- finish phase
+            int item2 = item;
+            asm volatile("" : "+r"(item2));      // opaque: do not carry scan / n / p0 through the stream phase in registers
+            int scan, parts, n;
+            int64_t p0;
+            sc_item<SPLIT>(item2, offsets, n_scans, sp, scan, parts, p0, n);
+            if constexpr (SPLIT) {
+                sc_finish_split<NT, SC_DU>(srows, gp, ns, r0, R, S, scan, parts, sp.done, &s_last);
+            } else if constexpr (SC_SLOT) {
+                sc_finish_slot<NT, SC_DU>(srows, gp, out + (size_t)scan * cells, ns, r0, R, S);
+            } else {
+                const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;
+                const uint2 *wseg = spill + (size_t)blockIdx.x * spill_cap + (size_t)(tid >> 5) * seg;
+                sc_finish_scan<NT>(srows, sm.base, out + (size_t)scan * cells, ns, r0, R, S, wseg,
+                                   (int)(reinterpret_cast<const uint2 *>(gp) - wseg));
+            }
+        }
         par ^= 1;
         item = s_next[par];                      // published by the barriers of the finish
+    }
+}
+
+// ---- k1_probe: where to put the resident window -------------------------------------------------------------
+// Ring histogram of PROBE_BLOCKS * PROBE_THREADS * PROBE_PPT pseudo-randomly sampled points of the batch; the last
+// block to finish picks the start ring r0 of the window of `nwin` rings that holds the most samples (ring R-1, the
+// clamp ring, is resident anyway and not part of the search) and writes it to *window.  A heuristic only: the grids
+// do not depend on r0.  probe[] = ring histogram [R], then the finished-blocks counter; zeroed before the launch.
+constexpr int PROBE_BLOCKS = 32, PROBE_THREADS = 256, PROBE_PPT = 8, PROBE_MAXR = 4096;
+
+__global__ void __launch_bounds__(PROBE_THREADS)
+k1_probe(const uint8_t *__restrict__ pts, const int64_t first, const int64_t total, const float inv_gap_ring, const int R,
+         const int nwin, unsigned int *__restrict__ probe, int *__restrict__ window)
+{
+    __shared__ unsigned int sh[PROBE_MAXR];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < R; i += PROBE_THREADS) sh[i] = 0u;
+    __syncthreads();
+    const float4 *p4 = reinterpret_cast<const float4 *>(pts) + first;
+#pragma unroll
+    for (int k = 0; k < PROBE_PPT; ++k) {
+        const uint32_t g = (uint32_t)((blockIdx.x * PROBE_THREADS + tid) * PROBE_PPT + k);
+        const uint64_t idx = ((uint64_t)(g * 2654435761u) * (uint64_t)total) >> 32;       // uniform over the batch
+        const float4 v = ld_stream_f4(p4 + idx);
+        const float r = sqrtf(v.x * v.x + v.y * v.y) * inv_gap_ring;
+        if (r == r) atomicAdd(&sh[r >= (float)(R - 1) ? R - 1 : (int)r], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < R; i += PROBE_THREADS)
+        if (sh[i]) atomicAdd(probe + i, sh[i]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        s_last = atomicAdd(probe + R, 1u) == gridDim.x - 1;
+        if (s_last) __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    for (int i = tid; i < R; i += PROBE_THREADS) sh[i] = __ldcg(probe + i);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int cur = 0, best;
+        for (int i = 0; i < nwin; ++i) cur += sh[i];
+        best = cur;
+        int r0 = 0;
+        for (int s = 1; s + nwin <= R - 1; ++s) {                 // windows [s, s + nwin) below the clamp ring
+            cur += sh[s + nwin - 1] - sh[s - 1];
+            if (cur > best) { best = cur; r0 = s; }
+        }
+        *window = r0;
     }
 }

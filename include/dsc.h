@@ -98,6 +98,8 @@ float dsc_last_kernel_ms(const dsc_ctx *ctx);
  *                    1 = generic L2-key kernels only, 3 = k1_scan whenever the shape allows
  *   "sc_cfg"         k1_scan launch shape: 0 = 768 threads x 3 loads, 1 = 1024 x 3, 2 = 1024 x 2
  *   "sc_smem_rows"   resident ring rows of k1_scan (-1 = as many as the carve-out allows)
+ *   "sc_window"      first ring of k1_scan's resident window (-1 = chosen per call by k1_probe from a ring histogram
+ *                    of sampled points; the grids never depend on it)
  *   "sc_split"       -1 = auto, 0 = never cut scans into work items, 1 = always
  *   "sc_item_points" target points per work item when scans are cut (default 131072)
  *   "no_defgrid"     1 = do not use the default-grid specialisation of k1_scan */
