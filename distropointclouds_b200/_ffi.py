@@ -21,7 +21,7 @@ EXPORTS = (
     "dsc_kernel_launches", "dsc_set_option", "dsc_host_alloc", "dsc_host_free", "dsc_sc_build_batch",
     "dsc_sc_build_batch_f64", "dsc_sc_normalize01",
     "dsc_set_polar_tables", "dsc_raster_boxes", "dsc_reconstruct_batch", "dsc_covered_mask",
-    "dsc_gather_cells",
+    "dsc_gather_cells", "dsc_label_maps", "dsc_label_heatmap", "dsc_voxel_downsample",
 )
 
 
@@ -70,6 +70,16 @@ def load() -> C.CDLL:
         from . import build as _build
         _build.build()          # raises if nvcc is unavailable -- no fallback
     L = C.CDLL(LIB_PATH)
+    if os.environ.get("DSC_LIB"):
+        # A/B builds (profiles/microbench/build_variant.sh, older revisions) may lack newer entry points: bind what exists
+        class _Missing:
+            argtypes = restype = None
+
+            def __call__(self, *a):
+                raise DscError(DSC_ERR_INVALID, "this DSC_LIB build does not export the entry point")
+        for name in EXPORTS:
+            if not hasattr(L, name):
+                setattr(L, name, _Missing())
     vp, ip = C.c_void_p, C.c_int
     L.dsc_version.restype = C.c_char_p
     L.dsc_create.argtypes = [ip, C.POINTER(vp)]
@@ -92,6 +102,9 @@ def load() -> C.CDLL:
     L.dsc_reconstruct_batch.argtypes = [vp, vp, ip, ip, C.c_double, ip, vp, vp, vp, C.c_int64, vp]
     L.dsc_covered_mask.argtypes = [vp, vp, C.c_int64, vp, C.c_int64, ip, vp, vp]
     L.dsc_gather_cells.argtypes = [vp, vp, vp, C.c_int64, ip, vp, vp]
+    L.dsc_label_maps.argtypes = [vp, vp, vp, vp, vp, ip, ip, ip, ip, ip, ip, vp, vp, vp]
+    L.dsc_label_heatmap.argtypes = [vp, vp, vp, ip, ip, ip, ip, vp, ip, ip, vp, vp]
+    L.dsc_voxel_downsample.argtypes = [vp, vp, C.c_int64, ip, ip, C.c_double, ip, vp, C.c_int64, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:      # default restype

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdsc.so")
-SOURCES = ["dsc_api.cu", "dsc_k1_build.cu", "dsc_k1_f64.cu", "dsc_k23_cells.cu"]
+SOURCES = ["dsc_api.cu", "dsc_k1_build.cu", "dsc_k1_f64.cu", "dsc_k23_cells.cu", "dsc_k6_labels.cu", "dsc_k7_voxel.cu"]
 HEADERS = ["dsc_internal.h", "dsc_math.cuh", "dsc_k1_common.cuh", "dsc_k1_scan.cuh", "dsc_k1_fallback.cuh", "dsc_k4.cuh", "dsc_math_f64.cuh",
            os.path.join("..", "..", "include", "dsc.h")]
 

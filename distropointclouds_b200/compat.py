@@ -78,6 +78,14 @@ def _scan_context_b(self, pts_xyz):
     return grid
 
 
+def _downsample_voxel(pts_xyz, voxel):
+    """scan_context_node.py:93-100 on K7 (Open3D's published algorithm, parity unpinned; output sorted by voxel)."""
+    pts = np.asarray(pts_xyz)
+    if pts.size == 0:
+        return pts_xyz
+    return default_engine(device).voxel_downsample_host(pts, float(voxel))[0]
+
+
 def _rec_sc_to_pointcloud(self, sc_data):
     """reconstruct_pointcloud.py:47-77 on K3 (returns points, colors, bin_ids)."""
     sc = np.asarray(sc_data)
@@ -126,8 +134,10 @@ def _candidates(modules: Optional[Iterable[object]]):
             if m is not None and not getattr(m, "__name__", "").startswith("distropointclouds_b200")]
 
 
-def install(modules: Optional[Iterable[object]] = None, device_index: int = 0) -> Dict[str, List[str]]:
-    """Patch every reference class found.  Returns {module name: [patched attributes]}."""
+def install(modules: Optional[Iterable[object]] = None, device_index: int = 0,
+            patch_voxel: bool = True) -> Dict[str, List[str]]:
+    """Patch every reference class found.  Returns {module name: [patched attributes]}.
+    patch_voxel=False leaves ScanContextComputer._downsample_voxel to Open3D (where it is installed)."""
     global device
     device = int(device_index)
     done: Dict[str, List[str]] = {}
@@ -155,6 +165,9 @@ def install(modules: Optional[Iterable[object]] = None, device_index: int = 0) -
             seen.add(comp)
             _patch(comp, "_scan_context", _scan_context_b)
             names.append("ScanContextComputer._scan_context")
+            if patch_voxel and "_downsample_voxel" in comp.__dict__:
+                _patch(comp, "_downsample_voxel", staticmethod(_downsample_voxel))
+                names.append("ScanContextComputer._downsample_voxel")
         rec = d.get("ScanContextReconstructor")
         if isinstance(rec, type) and rec.__module__ == getattr(m, "__name__", None) and rec not in seen \
                 and "scan_context_to_pointcloud" in rec.__dict__:

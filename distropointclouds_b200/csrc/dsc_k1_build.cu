@@ -240,13 +240,17 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         unsigned long long *stp = (unsigned long long *)stats;
         const bool full = p->full_height != 0;
         const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
+#define SC_LAUNCH5(F, V, H, U, NT, D, SP, ST)                                                                   \
+    do {                                                                                                        \
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP, ST>,                                  \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
+        k1_scan<F, V, H, U, NT, D, SP, ST><<<ctas, NT, sc_smem, st>>>(pts, d_offsets, n_scans,                  \
+                                                                      (uint2 *)ctx->spill, spill_cap, out, stp, \
+                                                                      cursor, ns, window, cfg, spa);            \
+    } while (0)
 #define SC_LAUNCH4(F, V, H, U, NT, D, SP)                                                                       \
     do {                                                                                                        \
-        DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP>,                                      \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));         \
-        k1_scan<F, V, H, U, NT, D, SP><<<ctas, NT, sc_smem, st>>>(pts, d_offsets, n_scans, (uint2 *)ctx->spill, \
-                                                                  spill_cap, out, stp, cursor, ns, window, cfg, \
-                                                                  spa);                                         \
+        if (stp) SC_LAUNCH5(F, V, H, U, NT, D, SP, true); else SC_LAUNCH5(F, V, H, U, NT, D, SP, false);        \
     } while (0)
 #define SC_LAUNCH3(F, V, H, U, NT, D)                                                                           \
     do {                                                                                                        \
@@ -271,6 +275,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
 #undef SC_LAUNCH_DEF
 #undef SC_LAUNCH3
 #undef SC_LAUNCH4
+#undef SC_LAUNCH5
         if ((rc = dsc_check_launch(ctx, "k1_scan"))) return rc;
         if (out_norm) return normalize_device(ctx, out, n_scans, cells, out_norm, st);
         return DSC_OK;

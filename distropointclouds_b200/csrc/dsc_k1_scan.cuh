@@ -83,35 +83,63 @@ __device__ __forceinline__ uint4 ld_spill2(const uint2 *p)
     return v;
 }
 
+// max-reduce `key` into the shared-memory cell at `addr` when `doit`: LDS pre-check (most points are not a new maximum)
+// + ATOMS.MAX, predicated instead of branched.
+// `w` is the point's intensity word -- dead data, but it doubles as the destination of the LDS: that keeps its register
+// occupied from the 128-bit point load until here.  Otherwise ptxas hands the (dead) fourth register of the in-flight
+// load to some early instruction of the PREVIOUS point, which then waits for the whole load (a write-after-write on
+// the long scoreboard: one POPC held 20 % of all stall samples in profiles/r2d) and defeats the register ping-pong.
+__device__ __forceinline__ void smem_max_if(const uint32_t addr, const uint32_t key, const bool doit, uint32_t w)
+{
+    asm volatile("{\n"
+                 ".reg .pred p, q;\n"
+                 "setp.ne.u32 p, %3, 0;\n"
+                 "@p ld.shared.u32 %0, [%1];\n"
+                 "setp.gt.and.u32 q, %2, %0, p;\n"
+                 "@q red.shared.max.u32 [%1], %2;\n"
+                 "}" : "+r"(w) : "r"(addr), "r"(key), "r"((uint32_t)doit) : "memory");
+}
+
+__device__ __forceinline__ uint32_t sc_tok3(const float a, const float b, const float c)
+{
+    uint32_t t;
+    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(t) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)));
+    return t;
+}
+__device__ __forceinline__ uint32_t sc_tok2(const float a, const float b)
+{
+    uint32_t t;
+    asm volatile("xor.b32 %0, %1, %2;" : "=r"(t) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+    return t;
+}
+
 // Fold one binned point into the key grid.  Called warp-uniformly; `valid` masks lanes without a point.
-//   resident cell      LDS pre-check + ATOMS.MAX (most points are not a new maximum)
-//   any other cell     SPILL: appended to the warp's spill list (`gp` is the list's write pointer, advanced for the whole
-//                      warp);  !SPILL (split items): RED.MAX straight into the scan's key grid (`gp` is that grid)
+//   resident cell      LDS pre-check + ATOMS.MAX
+//   any other cell     SPILL: appended to the warp's spill list (`gbase` = this CTA's list region, `goff` = the warp's
+//                      write position in it, in entries, advanced for the whole warp; `lt` = %lanemask_lt);
+//                      !SPILL (split items): RED.MAX straight into the scan's key grid (`gbase`)
 template <bool FULL, bool SPILL>
-__device__ __forceinline__ void sc_commit(const float zv, const int cell, bool valid, const SmemRows sm, uint32_t *&gp)
+__device__ __forceinline__ void sc_commit(const float zv, const int cell, bool valid, const SmemRows sm, uint32_t *const gbase, uint32_t &goff,
+                                          const unsigned lt, const uint32_t w = 0u)
 {
     const uint32_t u = __float_as_uint(zv);
     const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
     valid = valid && (zv == zv);                 // NaN never wins (scaner_version2.py:107)
     if (!FULL) valid = valid && (zv > 0.0f);     // offset mode: cells start at 0, strict '>'
-    const bool win = (uint32_t)(cell - sm.c0) < (uint32_t)sm.lim;               // rings r0 .. r0+ns-2
+    const int rel = cell - sm.c0;
+    const bool win = (uint32_t)rel < (uint32_t)sm.lim;                          // rings r0 .. r0+ns-2
     const bool res = win || cell >= sm.last;
-    if (valid && res) {
-        const int local = win ? cell - sm.c0 : cell + sm.shift;                 // clamp ring -> row ns-1
-        const uint32_t addr = sm.base + (uint32_t)local * 4u;
-        if (key > lds_u32(addr)) reds_max_u32(addr, key);
-    }
+    const int local = win ? rel : cell + sm.shift;                              // clamp ring -> row ns-1
+    smem_max_if(sm.base + (uint32_t)local * 4u, key, valid && res, w);
     if constexpr (SPILL) {
-        const unsigned m = __ballot_sync(0xffffffffu, valid && !res);
-        if (m) {                                 // warp-uniform
-            uint2 *w = reinterpret_cast<uint2 *>(gp);
+        const bool sp = valid && !res;
+        const unsigned m = __ballot_sync(0xffffffffu, sp);
 #ifndef SC_TIMING_NO_SPILL                       // (timing experiments only: wrong grids)
-            if (valid && !res) st_spill(w + __popc(m & lanemask_lt()), (uint32_t)cell, key);
+        if (sp) st_spill(reinterpret_cast<uint2 *>(gbase) + (goff + __popc(m & lt)), (uint32_t)cell, key);
 #endif
-            gp = reinterpret_cast<uint32_t *>(w + __popc(m));
-        }
+        goff += __popc(m);
     } else {
-        if (valid && !res) red_max_global(gp + cell, key);
+        if (valid && !res) red_max_global(gbase + cell, key);
     }
 }
 
@@ -135,8 +163,8 @@ __device__ __noinline__ uint2 sc_exact_queued(uint32_t qaddr, const ExactArgs *_
 // run the exact chain for the queue entries [first, first + count) of this warp (count <= 32) and commit them
 template <int VARIANT, bool FULL, bool SPILL>
 __device__ __forceinline__ void sc_exact_batch(const uint32_t queue, const unsigned first, const unsigned count,
-                                               const ExactArgs *ea, uint32_t *&gp, unsigned &n_clamped,
-                                               unsigned long long *__restrict__ st, const SmemRows sm)
+                                               const ExactArgs *ea, uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped,
+                                               unsigned long long *__restrict__ st, const SmemRows sm, const unsigned lt)
 {
     const unsigned lane = threadIdx.x & 31u;
     const bool mine = lane < count;
@@ -146,36 +174,37 @@ __device__ __forceinline__ void sc_exact_batch(const uint32_t queue, const unsig
     __syncwarp();
     const int status = (int)(b.x >> 27);
     n_clamped += (mine && status == dsc::PT_CLAMPED) ? 1u : 0u;
-    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED, sm, gp);
+    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED, sm, gbase, goff, lt);
 }
 
 // One point per lane, called warp-uniformly (`active` masks lanes past the end of the item).
-// (`qoff`: byte offset of the exact-path queues from the rows; the warp's own queue address is only formed on the rare path)
-template <int VARIANT, bool FULL, bool DEF, bool SPILL>
+// `qoff`: byte offset of the exact-path queues from the rows; the warp's own queue address and the scan's counter block
+// are only formed on the rare paths.  STATS = false: no per-scan counters are kept at all (stats == NULL).
+template <int VARIANT, bool FULL, bool DEF, bool SPILL, bool STATS>
 __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v, const bool active,
-                                         uint32_t *&gp, unsigned &n_clamped, unsigned long long *__restrict__ stats,
-                                         const int scan, const SmemRows sm, const uint32_t qoff, unsigned &qcount)
+                                         uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped, unsigned long long *__restrict__ stats,
+                                         const int scan, const SmemRows sm, const uint32_t qoff, unsigned &qcount,
+                                         const unsigned lt, const uint32_t wtok = 0u)
 {
-    unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
     int ring, sector;
     bool beyond;
     bool ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
     if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
     bool take = ok && active;
     if (VARIANT == 1) {
-        if (take && beyond && st) atomicAdd(st + 4, 1ull);   // r > max_length: dropped (scan_context_node.py:134-137)
+        if (STATS && take && beyond)                         // r > max_length: dropped (scan_context_node.py:134-137)
+            atomicAdd(stats + (int64_t)scan * DSC_STATS_WORDS + 4, 1ull);
         take = take && !beyond;
-    } else {
+    } else if (STATS) {
         n_clamped += (take && beyond) ? 1u : 0u;
     }
     const int S = DEF ? dsc::defgrid::S : cfg.S;
-    sc_commit<FULL, SPILL>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, take, sm, gp);
+    sc_commit<FULL, SPILL>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, take, sm, gbase, goff, lt, wtok);
     const unsigned m = __ballot_sync(0xffffffffu, active && !ok);
     if (m) {                                     // warp-uniform, rare
-        const unsigned lane = threadIdx.x & 31u;
         const uint32_t queue = sm.base + qoff + (threadIdx.x >> 5) * SCQ_WARP_BYTES;
         if (active && !ok) {
-            const uint32_t a = queue + (qcount + __popc(m & ((1u << lane) - 1u))) * 4u;
+            const uint32_t a = queue + (qcount + __popc(m & lt)) * 4u;
             sts_f32(a, v.x);
             sts_f32(a + SCQ_CAP * 4, v.y);
             sts_f32(a + SCQ_CAP * 8, v.z);
@@ -183,16 +212,17 @@ __device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea,
         qcount += __popc(m);
         if (qcount >= 32u) {
             qcount -= 32u;
-            sc_exact_batch<VARIANT, FULL, SPILL>(queue, qcount, 32u, ea, gp, n_clamped, st, sm);
+            unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
+            sc_exact_batch<VARIANT, FULL, SPILL>(queue, qcount, 32u, ea, gbase, goff, n_clamped, st, sm, lt);
         }
     }
 }
 
 // exact-only flavour (DSC_FLAG_EXACT_ONLY, non-dyadic gaps): every point takes the fdlibm chain
 template <int VARIANT, bool FULL, bool SPILL>
-__device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4 v, const bool active, uint32_t *&gp,
+__device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4 v, const bool active, uint32_t *const gbase, uint32_t &goff,
                                                unsigned &n_clamped, unsigned long long *__restrict__ stats, const int scan,
-                                               const SmemRows sm)
+                                               const SmemRows sm, const unsigned lt)
 {
     unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
     uint2 b = make_uint2((uint32_t)dsc::PT_NONFINITE << 27, 0u);
@@ -208,18 +238,18 @@ __device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4
     __syncwarp();
     const int status = (int)(b.x >> 27);
     n_clamped += (active && status == dsc::PT_CLAMPED) ? 1u : 0u;
-    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), active && status <= dsc::PT_CLAMPED, sm, gp);
+    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), active && status <= dsc::PT_CLAMPED, sm, gbase, goff, lt);
 }
 
 // end of item: the queue's remaining entries (fewer than 32)
 template <int VARIANT, bool FULL, bool SPILL>
-__device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *&gp, unsigned &n_clamped,
+__device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped,
                                          unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t qoff,
-                                         unsigned &qcount)
+                                         unsigned &qcount, const unsigned lt)
 {
     if (qcount) {                                // warp-uniform
         const uint32_t queue = sm.base + qoff + (threadIdx.x >> 5) * SCQ_WARP_BYTES;
-        sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gp, n_clamped, st, sm);
+        sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gbase, goff, n_clamped, st, sm, lt);
         qcount = 0;
     }
 }
@@ -423,7 +453,7 @@ __device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, ui
 //   spill       whole-scan items: [gridDim.x][spill_cap] (cell, key) pairs, one region per CTA, cut into per-warp lists
 //   spill_cap   entries per CTA: >= ceil(max points per scan / NT) * NT
 //   window      device int: first ring of the resident window, written by k1_probe earlier in the stream
-template <bool FAST, int VARIANT, bool FULL, int U, int NT, bool DEF, bool SPLIT>
+template <bool FAST, int VARIANT, bool FULL, int U, int NT, bool DEF, bool SPLIT, bool STATS>
 __global__ void __launch_bounds__(NT, 1)
 k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, int n_scans,
         uint2 *__restrict__ spill, const size_t spill_cap, float *__restrict__ out, unsigned long long *__restrict__ stats,
@@ -450,6 +480,10 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     const int r0 = *window;                      // first ring of the resident window (k1_probe): 0 <= r0 <= R - ns
     SmemRows sm;
     sm.base = (uint32_t)__cvta_generic_to_shared(srows);
+    // keep both in registers: passed through a shuffle, which ptxas cannot re-derive in the loop (re-reading
+    // SR_LTMASK or rebuilding the shared-window address costs 1-5 instructions per point in an issue-bound loop)
+    sm.base = __shfl_sync(0xffffffffu, sm.base, 0);
+    const unsigned lt = __shfl_sync(0xffffffffu, lanemask_lt(), (int)(tid & 31));
     sm.c0 = r0 * S;
     sm.lim = (ns - 1) * S;                       // host guarantees ns >= 2
     sm.last = (R - 1) * S;
@@ -468,20 +502,23 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     while (item < n_items) {
         // work item after this one: fetched now, consumed after the item (the round trip is hidden)
         if (tid == 0) s_next[par ^ 1] = (int)atomicAdd(cursor, 1u);
-        // gp: split items -- the scan's key grid (== its output grid); whole scans -- write pointer of this warp's spill list
-        uint32_t *gp;
+        // gbase / goff: split items -- the scan's key grid (== its output grid); whole scans -- this CTA's spill region
+        // (CTA-uniform: lives in uniform registers) and this warp's write position in it (one register)
+        uint32_t *gbase;
+        uint32_t goff = 0;
         {   // ---- stream phase.  Nothing but the loop state may stay live here (80 registers): the item's facts
             // (scan, first point, count) are recomputed for the finish instead of being carried through the loop.
             int scan, parts, n;
             int64_t p0;
             sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
             if constexpr (SPLIT) {
-                gp = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
+                gbase = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
             } else if constexpr (SC_SLOT) {
-                gp = reinterpret_cast<uint32_t *>(spill) + (size_t)blockIdx.x * (size_t)cells;
+                gbase = reinterpret_cast<uint32_t *>(spill) + (size_t)blockIdx.x * (size_t)cells;
             } else {
                 const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;       // most points one warp can see
-                gp = reinterpret_cast<uint32_t *>(spill + (size_t)blockIdx.x * spill_cap + (size_t)(tid >> 5) * seg);
+                gbase = reinterpret_cast<uint32_t *>(spill + (size_t)blockIdx.x * spill_cap);
+                goff = (uint32_t)(tid >> 5) * seg;
             }
             // the stream position is a 32-bit index of 16-byte rows from `pts` (host guarantees < 2^32 rows per call):
             // one register across the loop instead of a 64-bit pointer
@@ -491,11 +528,17 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             uint32_t p = (uint32_t)p0 + (uint32_t)tid;
             float4 a[U], b[U];
 #define SC_LD(idx) ld_stream_f4_hint(pts4 + (idx), pol_stream)
-#define SC_PT(v, act)                                                                                           \
+#define SC_PT(v, act, tok)                                                                                         \
     do {                                                                                                        \
-        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, SPILL>(cfg, &s_ea, (v), (act), gp, n_clamped, stats, scan, sm, qoff, qcount); \
-        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v), (act), gp, n_clamped, stats, scan, sm);          \
+        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, SPILL, STATS>(cfg, &s_ea, (v), (act), gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt, (tok)); \
+        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v), (act), gbase, goff, n_clamped, stats, scan, sm, lt);      \
     } while (0)
+            // SC_TOK: one real use of the (dead) intensity words of a register set when its processing starts.  Without it
+            // ptxas hands those registers -- the fourth destination registers of 128-bit loads that are still in
+            // flight -- to instructions of the set processed BEFORE, which then wait for the whole load (write-after-
+            // write on the long scoreboard: one POPC held 20 % of all stall samples in profiles/r2d_*) and the register
+            // ping-pong is defeated.  The XOR of the words becomes the scratch destination of the first point's LDS.
+#define SC_TOK(s) (U == 3 ? sc_tok3((s)[0].w, (s)[1].w, (s)[2].w) : sc_tok2((s)[0].w, (s)[U - 1].w))
             if (nfull > 0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
@@ -504,32 +547,36 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             while (step + 1 < nfull) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * NT);
+                const uint32_t ta = SC_TOK(a);
 #pragma unroll
-                for (int u = 0; u < U; ++u) SC_PT(a[u], true);
+                for (int u = 0; u < U; ++u) SC_PT(a[u], true, u == 0 ? ta : 0u);
                 p += 2 * STEP;
                 step += 2;
                 if (step < nfull) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
                 }
+                const uint32_t tb = SC_TOK(b);
 #pragma unroll
-                for (int u = 0; u < U; ++u) SC_PT(b[u], true);
+                for (int u = 0; u < U; ++u) SC_PT(b[u], true, u == 0 ? tb : 0u);
             }
             if (step < nfull) {
+                const uint32_t ta = SC_TOK(a);
 #pragma unroll
-                for (int u = 0; u < U; ++u) SC_PT(a[u], true);
+                for (int u = 0; u < U; ++u) SC_PT(a[u], true, u == 0 ? ta : 0u);
             }
+#undef SC_TOK
             for (int i0 = nfull * STEP; i0 < n; i0 += NT) {       // ragged tail, warp-uniform trip count
                 const bool act = i0 + tid < n;
                 float4 v = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
                 if (act) v = SC_LD((uint32_t)p0 + (uint32_t)(i0 + tid));
-                SC_PT(v, act);
+                SC_PT(v, act, 0u);
             }
-            unsigned long long *st = stats ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
-            if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gp, n_clamped, st, sm, qoff, qcount);
+            unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
+            if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gbase, goff, n_clamped, st, sm, qoff, qcount, lt);
 #undef SC_LD
 #undef SC_PT
-            if (stats) {
+            if (STATS) {
                 const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
                 if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
                 if (tid == 0 && n) atomicAdd(st + 0, (unsigned long long)n);
@@ -542,14 +589,14 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             int64_t p0;
             sc_item<SPLIT>(item2, offsets, n_scans, sp, scan, parts, p0, n);
             if constexpr (SPLIT) {
-                sc_finish_split<NT, SC_DU>(srows, gp, ns, r0, R, S, scan, parts, sp.done, &s_last);
+                sc_finish_split<NT, SC_DU>(srows, gbase, ns, r0, R, S, scan, parts, sp.done, &s_last);
             } else if constexpr (SC_SLOT) {
-                sc_finish_slot<NT, SC_DU>(srows, gp, out + (size_t)scan * cells, ns, r0, R, S);
+                sc_finish_slot<NT, SC_DU>(srows, gbase, out + (size_t)scan * cells, ns, r0, R, S);
             } else {
                 const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;
-                const uint2 *wseg = spill + (size_t)blockIdx.x * spill_cap + (size_t)(tid >> 5) * seg;
-                sc_finish_scan<NT>(srows, sm.base, out + (size_t)scan * cells, ns, r0, R, S, wseg,
-                                   (int)(reinterpret_cast<const uint2 *>(gp) - wseg));
+                const uint32_t w0 = (uint32_t)(tid >> 5) * seg;
+                sc_finish_scan<NT>(srows, sm.base, out + (size_t)scan * cells, ns, r0, R, S,
+                                   spill + (size_t)blockIdx.x * spill_cap + w0, (int)(goff - w0));
             }
         }
         par ^= 1;

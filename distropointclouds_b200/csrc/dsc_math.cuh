@@ -341,6 +341,7 @@ DSC_HD float approx_sqrt(float s, float) { float r; asm("sqrt.approx.ftz.f32 %0,
 DSC_HD float approx_rcp(float s, float) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s)); return r; }
 DSC_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 DSC_HD float round_nearest(float a) { return rintf(a); }
+DSC_HD int f2i_sat(float a, float hi) { (void)hi; return __float2int_rz(a); }    // cvt.rzi saturates; NaN -> 0
 #else
 // host emulation for tests/host_math.cpp: correctly rounded value perturbed by `noise` * 2^-22
 // (|noise| <= 1 covers the documented MUFU error), with flush-to-zero of subnormal operands/results
@@ -360,6 +361,7 @@ DSC_HD float approx_rcp(float s, float noise)
 }
 DSC_HD float ffma(float a, float b, float c) { return (float)((double)a * (double)b + (double)c); }
 DSC_HD float round_nearest(float a) { return nearbyintf(a); }
+DSC_HD int f2i_sat(float a, float hi) { return (int)fminf(a, hi); }              // same values wherever the screen says ok
 #endif
 
 // Core of the screen: true when (ring, sector, beyond) are certain; false sends the point to bin_exact.
@@ -411,7 +413,7 @@ DSC_HD bool screened_core_t(const BinCfg &c, float x, float y, float noise_r, fl
     const bool far_out = qr >= Rp1;                      // deep in the clamp / reject zone
     const bool ok = (ds > (DEF ? defgrid::fast_ds : c.fast_ds)) &&
                     (far_out || dr > (DEF ? defgrid::fast_dr : c.fast_dr)) && (qr < INFINITY);
-    const int ir = (int)fminf(qr, Rp1);                  // qr >= 0: truncation == floor; clamped so the cast is defined
+    const int ir = f2i_sat(qr, Rp1);                     // qr >= 0: truncation == floor; saturating, so the cast is defined
     *beyond = ir >= Rr;
     *ring = min_i(ir, Rr - 1);
     *sector = (int)qs;

@@ -370,6 +370,55 @@ class Engine:
                                                     _ptr(pts_out), _ptr(bin_ids_out), int(pts_out.shape[0]),
                                                     C.c_void_p(stream)))
 
+    # -- K6 ------------------------------------------------------------------------------------
+    def label_maps_host(self, cells: np.ndarray, cell_offsets: np.ndarray, box_weight: Optional[np.ndarray] = None,
+                        box_frame: Optional[np.ndarray] = None, n_frames: int = 1, num_ring=160, num_sector=720,
+                        mode: int = 0, want_weight: bool = True):
+        """CSR covered cells of a batch of boxes -> (mask float32 (n_frames,R,S), weight float32 | None).
+        mode 0: out-of-grid cells ignored (tiny_sc_pred_v2.py:81); mode 1: clip ring, wrap sector (train_sc_ped.py:181-182)."""
+        c = np.ascontiguousarray(np.asarray(cells).reshape(-1, 2), dtype=np.int32)
+        offs = np.ascontiguousarray(cell_offsets, dtype=np.int64)
+        nb = offs.size - 1
+        w = np.ascontiguousarray(box_weight, dtype=np.float32) if (want_weight and box_weight is not None) else None
+        want_weight = want_weight and w is not None
+        fr = np.ascontiguousarray(box_frame, dtype=np.int32) if box_frame is not None else None
+        mask = np.empty((n_frames, num_ring, num_sector), np.float32)
+        weight = np.empty_like(mask) if want_weight else None
+        self._check(self._lib.dsc_label_maps(self._h, _ptr(c), _ptr(offs), _ptr(w), _ptr(fr), nb, int(n_frames),
+                                             int(num_ring), int(num_sector), int(mode), _ffi.MEM_HOST, _ptr(mask),
+                                             _ptr(weight), None))
+        return mask, weight
+
+    def label_heatmap_host(self, centers: np.ndarray, table: np.ndarray, center_frame: Optional[np.ndarray] = None,
+                           n_frames: int = 1, num_ring=160, num_sector=720) -> np.ndarray:
+        """(center_ring_idx, center_sector_idx) rows + the tabulated Gaussian -> float64 (n_frames,R,S) heat-maps."""
+        c = np.ascontiguousarray(np.asarray(centers).reshape(-1, 2), dtype=np.int32)
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        fr = np.ascontiguousarray(center_frame, dtype=np.int32) if center_frame is not None else None
+        heat = np.empty((n_frames, num_ring, num_sector), np.float64)
+        self._check(self._lib.dsc_label_heatmap(self._h, _ptr(c), _ptr(fr), c.shape[0], int(n_frames), int(num_ring),
+                                                int(num_sector), _ptr(t), int(t.size), _ffi.MEM_HOST, _ptr(heat), None))
+        return heat
+
+    # -- K7 ------------------------------------------------------------------------------------
+    def voxel_downsample_host(self, points: np.ndarray, voxel_size: float):
+        """Voxel-grid filter (Open3D's published voxel_down_sample algorithm; parity unpinned, see include/dsc.h):
+        (N,>=3) float32 or float64 points -> ((M,3) float64 voxel means sorted by voxel index, n_dropped non-finite)."""
+        p = np.asarray(points)
+        if p.ndim != 2 or p.shape[1] < 3:
+            raise ValueError("points must be (N,>=3)")
+        if p.dtype not in (np.float32, np.float64):
+            p = p.astype(np.float64)
+        if not p.flags.c_contiguous:
+            p = np.ascontiguousarray(p)
+        n = p.shape[0]
+        out = np.empty((max(n, 1), 3), np.float64)
+        n_out, n_drop = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.dsc_voxel_downsample(self._h, _ptr(p), n, int(p.dtype == np.float64), int(p.strides[0]),
+                                                   float(voxel_size), _ffi.MEM_HOST, _ptr(out), out.shape[0],
+                                                   C.byref(n_out), C.byref(n_drop), None))
+        return out[: n_out.value], int(n_drop.value)
+
     # -- K5 ------------------------------------------------------------------------------------
     def covered_mask_host(self, bin_ids: np.ndarray, cells: np.ndarray, num_ring=160, num_sector=720,
                           max_length=20.0) -> np.ndarray:

@@ -121,3 +121,71 @@ def build_mask_from_json(H: int, W: int, json_path: str) -> np.ndarray:
     ids = np.arange(H * W, dtype=np.int32)
     # mask[i] = i in {r*W+s}: the K5 membership kernel over the whole grid
     return eng.covered_mask_host(ids, c, H, W, float(SC.max_length)).astype(np.uint8).reshape(H, W)
+
+
+# ---- label-side training tensors --------------------------------------------------------------
+# The dataset classes of the reference rebuild these from the pedestrians_*.json lists in Python on every __getitem__;
+# here the per-cell work runs on the device (K6) and only the per-pedestrian scalars stay on the host.
+
+def pedestrian_weight(num_cells: int, distance: float) -> float:
+    """distro_model/tiny_sc_pred_v2.py:64-76 -- adaptive weight of one pedestrian (Python-float arithmetic)."""
+    if num_cells > 0:
+        size_weight = min(100.0 / num_cells, 5.0)
+        distance_weight = 1.0 + (distance / 20.0) ** 2
+        return min(size_weight * distance_weight, 10.0)
+    return 1.0
+
+
+def _csr_cells(ped_list):
+    cells = [np.asarray(p.get('covered_cells', []), dtype=np.int64).reshape(-1, 2) for p in ped_list]
+    offs = np.zeros(len(cells) + 1, np.int64)
+    np.cumsum([c.shape[0] for c in cells], out=offs[1:])
+    flat = np.concatenate(cells, axis=0) if cells else np.zeros((0, 2), np.int64)
+    return flat, offs
+
+
+def weight_and_mask_maps(ped_list, H: int = 160, W: int = 720, device=None):
+    """ScanContextPedestrianDataset.__getitem__'s mask and adaptive weight map (tiny_sc_pred_v2.py:57-85):
+    mask[r,s] = 1 on every in-range covered cell, weight[r,s] = max(1, weights of the pedestrians covering it).
+    Returns (mask float32 (H,W), weight_map float32 (H,W))."""
+    SC = _statics()
+    eng = default_engine(SC.device if device is None else device)
+    cells, offs = _csr_cells(ped_list)
+    w = np.array([pedestrian_weight(int(offs[i + 1] - offs[i]), p.get('distance', 10.0)) for i, p in enumerate(ped_list)],
+                 dtype=np.float64).astype(np.float32)
+    mask, weight = eng.label_maps_host(cells, offs, w, None, 1, H, W, mode=0, want_weight=True)
+    return mask[0], weight[0]
+
+
+def clip_wrap_mask(ped_list, H: int = 160, W: int = 720, device=None) -> np.ndarray:
+    """ScanContextPedDataset.__getitem__'s optional segmentation mask (train_sc_ped.py:175-183): ring indices
+    clipped to [0, H-1], sector indices wrapped with np.mod."""
+    SC = _statics()
+    eng = default_engine(SC.device if device is None else device)
+    cells, offs = _csr_cells(ped_list)
+    mask, _ = eng.label_maps_host(cells, offs, None, None, 1, H, W, mode=1, want_weight=False)
+    return mask[0]
+
+
+def gaussian_table(sigma: float, H: int = 160, W: int = 720) -> np.ndarray:
+    """exp(-0.5 * d2 / sigma**2) for the integer squared distances d2 = 0 .. (H-1)^2 + (W-1)^2, evaluated with the
+    expression of gaussian2d (train_sc_ped.py:78-79) and cut after the last non-zero value."""
+    d2 = np.arange((H - 1) ** 2 + (W - 1) ** 2 + 1)
+    with np.errstate(under="ignore"):
+        t = np.exp(-0.5 * d2 / (sigma ** 2))
+    nz = np.flatnonzero(t)
+    return np.ascontiguousarray(t[: int(nz[-1]) + 1] if nz.size else t[:1])
+
+
+def center_heatmap(ped_list, H: int = 160, W: int = 720, sigma: float = 1.8, device=None) -> np.ndarray:
+    """ScanContextPedDataset.__getitem__'s centre heat-map (train_sc_ped.py:165-173): np.maximum over the pedestrians
+    whose centre cell lies in the grid of gaussian2d((H,W), centre, sigma).  float64 as soon as one centre is valid
+    (np.maximum promotes), float32 zeros otherwise -- the reference's dtypes."""
+    centers = np.array([[int(p.get("center_ring_idx", -1)), int(p.get("center_sector_idx", -1))] for p in ped_list],
+                       dtype=np.int64).reshape(-1, 2)
+    ok = (centers[:, 0] >= 0) & (centers[:, 0] < H) & (centers[:, 1] >= 0) & (centers[:, 1] < W)
+    if not ok.any():
+        return np.zeros((H, W), dtype=np.float32)
+    SC = _statics()
+    eng = default_engine(SC.device if device is None else device)
+    return eng.label_heatmap_host(centers[ok], gaussian_table(sigma, H, W), None, 1, H, W)[0]

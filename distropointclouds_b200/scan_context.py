@@ -108,6 +108,8 @@ class ScanContext:
     # -- scaner_version2.py:117-178 / kitti_dataset.py:100-127 ------------------------------------
     def genSCs(self):
         ptcloud_xyz = self.load_velo_scan() if self.ptcloud_xyz is None else self.ptcloud_xyz
+        if bool(type(self).use_downsampling):                # scaner_version2.py:126-133: float64 voxel means (K7)
+            ptcloud_xyz, _ = type(self)._engine().voxel_downsample_host(np.asarray(ptcloud_xyz), float(type(self).downcell_size))
         SCs = []
         for res in range(len(type(self).sector_res)):
             num_sector = type(self).sector_res[res]
@@ -164,6 +166,20 @@ class ScanContextComputer:
         os.makedirs(self.output_dir, exist_ok=True)       # scan_context_node.py:57-58
         os.makedirs(self.dl_images_dir, exist_ok=True)
 
+    # -- scan_context_node.py:93-100 --------------------------------------------------------------
+    @staticmethod
+    def _downsample_voxel(pts_xyz: np.ndarray, voxel: float) -> np.ndarray:
+        """Open3D's voxel_down_sample on the GPU (K7): float64 voxel means, like np.asarray(d.points).  Open3D is not
+        installed here, so this restates its published algorithm (parity unpinned); the points come out sorted by
+        voxel index instead of in Open3D's hash-map order, which the scan context does not depend on."""
+        pts = np.asarray(pts_xyz)
+        if pts.size == 0:
+            return pts_xyz
+        out, _ = default_engine(ScanContextComputer.device_default).voxel_downsample_host(pts, float(voxel))
+        return out
+
+    device_default = 0
+
     # -- scan_context_node.py:102-157 -------------------------------------------------------------
     def _scan_context(self, pts_xyz: np.ndarray) -> np.ndarray:
         pts = np.asarray(pts_xyz)
@@ -175,9 +191,10 @@ class ScanContextComputer:
         self.last_stats = dict(zip(_STATS, (int(v) for v in stats)))
         return grid
 
-    # -- scan_context_node.py:159-188 (numeric part: grid + .npy; the PNG render is out of scope) --
+    # -- scan_context_node.py:159-188 (numeric part: down-sample, grid, .npy; the PNG render is out of scope) --
     def compute_and_save(self, pts_xyz: np.ndarray, stamp_stem: str):
-        sc = self._scan_context(pts_xyz)
+        pts_ds = self._downsample_voxel(pts_xyz, self.voxel_size)     # :161  float64 voxel means
+        sc = self._scan_context(pts_ds)                               # :168  binned in float64 -> float32 grid
         out_npy = os.path.join(self.output_dir, f"sc_{stamp_stem}.npy")
-        np.save(out_npy, sc.astype(np.float32))
+        np.save(out_npy, sc.astype(np.float32))                       # :185-186
         return sc, None, out_npy

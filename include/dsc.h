@@ -185,6 +185,52 @@ int dsc_covered_mask(dsc_ctx *ctx, const int32_t *bin_ids, int64_t n_ids, const 
 int dsc_gather_cells(dsc_ctx *ctx, const float *grid, const int32_t *cells, int64_t n_cells,
                      int mem, double *pts_out, void *stream);
 
+/* ---- K6: label-side training tensors ----------------------------------------
+ * Built on the device from the rasteriser's CSR output, so a dataset __getitem__ no longer walks JSON cell lists.
+ *
+ * dsc_label_maps: binary mask (+ optional adaptive weight map) of a batch of frames.
+ *   mode 0  cells outside the grid are ignored: ScanContextPedestrianDataset.__getitem__
+ *           (distro_model/tiny_sc_pred_v2.py:57-85) and build_mask_from_json (tiny_sc_ped.py:62-73)
+ *   mode 1  ring clipped to [0, R-1], sector wrapped with np.mod: ScanContextPedDataset.__getitem__
+ *           (distro_model/train_sc_ped.py:175-183)
+ *   cells / cell_offsets   the CSR lists dsc_raster_boxes writes ((ring, sector) int32 rows; int64 [n_boxes+1]);
+ *                          both live where `mem` says
+ *   box_weight   float32 [n_boxes]: min(min(100/num_cells, 5) * (1 + (distance/20)^2), 10) evaluated by the caller in
+ *                Python floats (tiny_sc_pred_v2.py:64-76) -- scalar host arithmetic, like a4/a6; may be NULL when
+ *                weight_out is NULL
+ *   box_frame    int32 [n_boxes] frame of each box, or NULL (all frame 0)
+ *   mask_out     float32 [n_frames][num_ring][num_sector]: 1 where any box covers the cell
+ *   weight_out   optional float32, same shape: max(1, largest box_weight covering the cell)
+ *
+ * dsc_label_heatmap: centre heat-map, np.maximum over the pedestrians of gaussian2d(center, sigma)
+ * (distro_model/train_sc_ped.py:74-79, :165-173; centres outside the grid are skipped, no sector wrap).
+ *   centers      int32 [n_centers][2] (center_ring_idx, center_sector_idx); center_frame int32 [n_centers] or NULL
+ *   table        HOST float64 [table_len]: exp(-0.5 * d2 / sigma**2) for the integer squared distances d2 = 0 ..
+ *                table_len-1, tabulated by the caller with NumPy exactly as gaussian2d evaluates it (cut where it
+ *                underflows to 0), so the heat-map is bit-identical to the reference's on any host
+ *   heat_out     float64 [n_frames][num_ring][num_sector] */
+int dsc_label_maps(dsc_ctx *ctx, const int32_t *cells, const int64_t *cell_offsets, const float *box_weight,
+                   const int32_t *box_frame, int n_boxes, int n_frames, int num_ring, int num_sector, int mode,
+                   int mem, float *mask_out, float *weight_out, void *stream);
+int dsc_label_heatmap(dsc_ctx *ctx, const int32_t *centers, const int32_t *center_frame, int n_centers,
+                      int n_frames, int num_ring, int num_sector, const double *table, int table_len, int mem,
+                      double *heat_out, void *stream);
+
+/* ---- K7: voxel-grid down-sampling ------------------------------------------------
+ * What the live node runs before every scan context: ScanContextComputer._downsample_voxel
+ * (scan_context_node.py:93-100), and the offline generator's use_downsampling branch (scaner_version2.py:126-133).
+ * Both call Open3D's PointCloud.voxel_down_sample, an un-vendored dependency that is not installed here: PARITY
+ * UNPINNED.  The kernel restates Open3D's published algorithm (float64: voxel_min_bound = min_bound - voxel/2; voxel
+ * index = floor((p - voxel_min_bound) / voxel); output = sum of the voxel's points in input order / count) and is
+ * deterministic.  Only the ORDER of the output points is ours (sorted by voxel index; Open3D iterates a hash map) -- the
+ * scan context built from them does not depend on it.  Non-finite points are dropped and counted.
+ *   pts       float32 (pts_f64 = 0; widened exactly, as Vector3dVector does) or float64 rows x,y,z
+ *   out_pts   float64 [cap][3]; *n_out = number of voxels (DSC_ERR_CAPACITY when cap is too small)
+ *   n_out / n_dropped   HOST int64 with DSC_MEM_HOST, DEVICE int64 with DSC_MEM_DEVICE (stream-ordered) */
+int dsc_voxel_downsample(dsc_ctx *ctx, const void *pts, int64_t n_points, int pts_f64, int pts_stride_bytes,
+                         double voxel_size, int mem, double *out_pts, int64_t cap, int64_t *n_out,
+                         int64_t *n_dropped, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

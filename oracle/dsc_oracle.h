@@ -51,6 +51,9 @@ int orc_point_bin_f64(const orc_params *p, double height_offset, double x, doubl
 int orc_sc_build_f64(const orc_params *p, double height_offset, const double *pts, int64_t n, int stride_doubles,
                      const double *theta_override, double *out64, float *out32, orc_stats *st, int64_t *n_boundary);
 
+int64_t orc_voxel_downsample(const double *pts, int64_t n, int stride_doubles, double voxel, double *out, int64_t cap,
+                             int64_t *n_dropped);
+
 void orc_normalize01(const float *grid, int64_t cells, float *out, float *mn_out, float *mx_out);
 
 int64_t orc_raster_box(int R, int S, const double *r_centers, const double *cos_tab,

@@ -92,6 +92,8 @@ def lib():
         L.orc_sc_build_f64.argtypes = [C.POINTER(OrcParams), C.c_double, dp, C.c_int64, C.c_int, dp, dp, fp,
                                        C.POINTER(OrcStats), lp]
         L.orc_sc_build_f64.restype = C.c_int
+        L.orc_voxel_downsample.argtypes = [dp, C.c_int64, C.c_int, C.c_double, dp, C.c_int64, lp]
+        L.orc_voxel_downsample.restype = C.c_int64
         L.orc_normalize01.argtypes = [fp, C.c_int64, fp, fp, fp]
         L.orc_normalize01.restype = None
         L.orc_raster_box.argtypes = [C.c_int, C.c_int, dp, dp, dp] + [C.c_double] * 6 + [ip, C.c_int64]
@@ -166,6 +168,19 @@ def sc_build_f64(points: np.ndarray, params: Params = Params(), theta_override=N
     d = st.as_dict()
     d["n_boundary"] = int(nb.value)
     return out, d
+
+
+def voxel_downsample(points: np.ndarray, voxel_size: float):
+    """Open3D's published voxel_down_sample algorithm (parity unpinned: Open3D is not installed), output sorted by
+    voxel index.  float32 input is widened exactly, as Vector3dVector does.  Returns ((M,3) float64, n_dropped)."""
+    pts = np.ascontiguousarray(np.asarray(points)[:, :3], dtype=np.float64)
+    out = np.empty((max(len(pts), 1), 3), np.float64)
+    nd = C.c_int64(0)
+    k = lib().orc_voxel_downsample(_p(pts, C.c_double), len(pts), 3, float(voxel_size), _p(out, C.c_double), len(out),
+                                   C.byref(nd))
+    if k < 0:
+        raise ValueError(f"orc_voxel_downsample rc={k}")
+    return out[:k].copy(), int(nd.value)
 
 
 def as_packed(points: np.ndarray):
@@ -278,3 +293,53 @@ def reconstruct(grid: np.ndarray, num_ring=160, num_sector=720, max_length=20.0,
                               _p(st, C.c_double), _p(g, C.c_float), int(bool(full_height)),
                               float(height_offset), _p(pts, C.c_double), _p(ids, C.c_int32), cap)
     return pts[:k].copy(), ids[:k].copy()
+
+
+# ---- label-side training tensors: plain NumPy/Python restatement of the reference loops --------
+
+def label_weight_mask(ped_list, H=160, W=720):
+    """ScanContextPedestrianDataset.__getitem__ (distro_model/tiny_sc_pred_v2.py:57-85): (mask, weight_map) float32."""
+    mask = np.zeros((H, W), dtype=np.float32)
+    weight_map = np.ones((H, W), dtype=np.float32)
+    for ped in ped_list:
+        covered = ped.get('covered_cells', [])
+        distance = ped.get('distance', 10.0)
+        num_cells = len(covered)
+        if num_cells > 0:
+            size_weight = min(100.0 / num_cells, 5.0)                        # :67
+            distance_weight = 1.0 + (distance / 20.0) ** 2                   # :70
+            ped_weight = min(size_weight * distance_weight, 10.0)            # :73
+        else:
+            ped_weight = 1.0
+        for r, s in covered:
+            if 0 <= r < H and 0 <= s < W:                                    # :81
+                mask[r, s] = 1.0
+                weight_map[r, s] = max(weight_map[r, s], ped_weight)         # float32 store of the float64 maximum
+    return mask, weight_map
+
+
+def label_clip_wrap_mask(ped_list, H=160, W=720):
+    """ScanContextPedDataset.__getitem__ (distro_model/train_sc_ped.py:175-183): ring clipped, sector np.mod-wrapped."""
+    mask = np.zeros((H, W), dtype=np.float32)
+    for ped in ped_list:
+        cells = np.array(ped.get("covered_cells", []), dtype=np.int32)
+        if cells.size:
+            rr = np.clip(cells[:, 0], 0, H - 1)
+            ss = np.mod(cells[:, 1], W)
+            mask[rr, ss] = 1.0
+    return mask
+
+
+def label_center_heatmap(ped_list, H=160, W=720, sigma=1.8):
+    """ScanContextPedDataset.__getitem__ (train_sc_ped.py:165-173) with gaussian2d (:74-79)."""
+    heat = np.zeros((H, W), dtype=np.float32)
+    rr = np.arange(H)[:, None]
+    ss = np.arange(W)[None, :]
+    for ped in ped_list:
+        r = int(ped.get("center_ring_idx", -1))
+        s = int(ped.get("center_sector_idx", -1))
+        if 0 <= r < H and 0 <= s < W:
+            d2 = (rr - r) ** 2 + (ss - s) ** 2
+            with np.errstate(under="ignore"):
+                heat = np.maximum(heat, np.exp(-0.5 * d2 / (sigma ** 2)))
+    return heat
