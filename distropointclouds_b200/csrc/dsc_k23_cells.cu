@@ -118,17 +118,21 @@ k3_rows(const float *__restrict__ grids, int n_grids, int R, int S, int full_hei
 }
 
 // ---- K3, single pass over HBM ---------------------------------------------------------------------
-// Persistent CTAs take grids in ticket order.  Pass A counts the kept cells of each ring row (the grid comes in
-// from HBM and stays in L2: 460 KB per CTA), a CTA-wide scan turns the counts into row offsets, the grid's base
-// offset comes from a decoupled look-back over the totals of the grids before it (they are owned by CTAs that
-// drew earlier tickets and are running, so the wait terminates), pass C re-reads the rows from L2 and writes the
-// points in row-major order.  HBM sees each grid once and each output byte once.
+// Persistent CTAs take grids in ticket order.  Pass A reads the grid once (128-bit loads, every load of a ring row in
+// flight at once), counts the kept cells of each row and COMPACTS them -- height and sector index -- into shared memory
+// (a grid keeps 15-30 % of its 115 200 cells: ~30 k entries of 6 bytes).  A CTA-wide scan turns the counts into row
+// offsets, the grid's base offset comes from a decoupled look-back over the totals of the grids before it (they are
+// owned by CTAs that drew earlier tickets and are running, so the wait terminates), and pass C expands the compacted
+// entries straight from shared memory into points, in row-major order, staged per warp so that they leave as
+// contiguous stores.  HBM sees each grid once and each output byte once, and nothing is re-read from L2 (round 1
+// re-read every row in pass C: 1.5x the algorithmic read traffic).  Rows that do not fit the compaction buffer
+// (unusually dense grids) are compacted and emitted in further rounds from L2.
 constexpr int K3F_THREADS = 1024;
-constexpr int K3F_CTAS_PER_SM = 1;                             // 2 x 512 threads measured 4 % slower
+constexpr int K3F_CTAS_PER_SM = 1;
 constexpr int K3F_WARPS = K3F_THREADS / 32;
 constexpr int K3F_MAXR = 2048;                                 // rows per grid the shared-memory scan can hold
-constexpr int K3F_MAXROUNDS = 8;                               // 128 cells per warp round: S <= 1024
-constexpr int K3F_STAGE_BYTES = 128 * 24 + 128 * 4;            // per-warp output staging
+constexpr int K3F_MAXROUNDS = 8;                               // 128 cells per warp round: S <= 1024 (sector fits 16 bits)
+constexpr int K3F_STAGE_BYTES = 32 * 24 + 32 * 4;              // per-warp output staging: 32 points
 constexpr unsigned long long K3F_AGG = 1ull << 62, K3F_PFX = 2ull << 62, K3F_VAL = (1ull << 62) - 1;
 
 // One ring row per warp at a time, read as 128-bit vectors with every load of the row in flight at once
@@ -142,49 +146,103 @@ __device__ __forceinline__ float4 k3_ld(const float4 *p, uint64_t pol)
     return v;
 }
 
+// pass A for one row: count the kept cells, claim room in the compaction buffer, write (height, sector) in row-major
+// order.  Returns the count; *pos_out = first entry, or -1 when the buffer is full (the row is done in a later round).
+template <int ROUNDS>
+__device__ __forceinline__ int k3_compact_row(const float4 *row, int rowvec, int full_height, uint64_t pol, int *s_alloc,
+                                              int zcap, float *zbuf, unsigned short *jbuf, int *pos_out)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    float4 v[ROUNDS];
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const int i = k * 32 + lane;
+        v[k] = i < rowvec ? k3_ld(row + i, pol) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    unsigned bal[ROUNDS][4];
+    int count = 0;
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) {
+        const float zc[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            bal[k][c] = __ballot_sync(0xffffffffu, full_height ? (zc[c] != 0.0f) : (zc[c] > 0.0f));
+            count += __popc(bal[k][c]);
+        }
+    }
+    int pos = 0;
+    if (lane == 0) {
+        pos = count ? atomicAdd(s_alloc, count) : 0;
+        if (pos + count > zcap) pos = -1;                  // (the claim stays: later rows of this round overflow too)
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    *pos_out = pos;
+    if (pos >= 0 && count) {
+        int before = 0;                                    // kept cells of the earlier rounds
+#pragma unroll
+        for (int k = 0; k < ROUNDS; ++k) {
+            const float zc[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+            int rank = pos + before + __popc(bal[k][0] & lt) + __popc(bal[k][1] & lt) + __popc(bal[k][2] & lt) +
+                       __popc(bal[k][3] & lt);             // kept cells of lower lanes come first, then lower components
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if ((bal[k][c] >> lane) & 1u) {
+                    zbuf[rank] = zc[c];
+                    jbuf[rank] = (unsigned short)(4 * (k * 32 + lane) + c);
+                    ++rank;
+                }
+            }
+            before += __popc(bal[k][0]) + __popc(bal[k][1]) + __popc(bal[k][2]) + __popc(bal[k][3]);
+        }
+    }
+    return count;
+}
+
 template <int ROUNDS>
 __global__ void __launch_bounds__(K3F_THREADS, K3F_CTAS_PER_SM)
 k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_height, float offset_f,
          const double *__restrict__ rcs, const double *__restrict__ cosT, const double *__restrict__ sinT,
          unsigned int *__restrict__ ticket, unsigned long long *__restrict__ status,
-         int64_t *__restrict__ item_offsets, double *__restrict__ pts_out, int32_t *__restrict__ ids_out, int64_t cap)
+         int64_t *__restrict__ item_offsets, double *__restrict__ pts_out, int32_t *__restrict__ ids_out, int64_t cap,
+         const int zcap)
 {
-    __shared__ int s_cnt[K3F_MAXR];
-    __shared__ int s_g;
+    __shared__ int s_g, s_alloc, s_left;
     __shared__ long long s_base;
-    extern __shared__ __align__(16) double k3_stage[];         // per warp: 128 x 3 doubles, then 128 ints
+    // dynamic: [per-warp staging][row offsets R+1][row buffer positions R][heights zcap][sectors zcap]
+    extern __shared__ __align__(16) double k3_smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    double *dbuf = k3_stage + (size_t)w * (K3F_STAGE_BYTES / 8);
-    int *ibuf = reinterpret_cast<int *>(dbuf + 384);
+    double *dbuf = k3_smem + (size_t)w * (K3F_STAGE_BYTES / 8);
+    int *ibuf = reinterpret_cast<int *>(dbuf + 96);
+    int *s_cnt = reinterpret_cast<int *>(k3_smem + (size_t)K3F_WARPS * (K3F_STAGE_BYTES / 8));
+    int *s_pos = s_cnt + (R + 1);
+    float *zbuf = reinterpret_cast<float *>(s_pos + R + ((R + 1 + R) & 1));
+    unsigned short *jbuf = reinterpret_cast<unsigned short *>(zbuf + zcap);
     const int rowvec = S >> 2;
-    const unsigned lt = (1u << lane) - 1u;
-    // pass A parks the grid in L2 (evict last), pass C lets go of it (evict first)
+    // pass A reads the grid once and lets go of it; rows that have to come back in a later round are parked in L2
     uint64_t pol_keep, pol_drop;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
     for (;;) {
-        if (tid == 0) s_g = (int)atomicAdd(ticket, 1u);
+        if (tid == 0) {
+            s_g = (int)atomicAdd(ticket, 1u);
+            s_alloc = 0;
+            s_left = 0;
+        }
         __syncthreads();
         const int g = s_g;
         if (g >= n_grids) break;
         const float4 *gp = reinterpret_cast<const float4 *>(grids + (size_t)g * R * S);
-        // ---- pass A: kept cells per row ----
+        // ---- pass A: count + compact every row ----
         for (int r = w; r < R; r += K3F_WARPS) {
-            const float4 *row = gp + (size_t)r * rowvec;
-            float4 v[ROUNDS];
-#pragma unroll
-            for (int k = 0; k < ROUNDS; ++k) {
-                const int i = k * 32 + lane;
-                v[k] = i < rowvec ? k3_ld(row + i, pol_keep) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            int pos;
+            const int count = k3_compact_row<ROUNDS>(gp + (size_t)r * rowvec, rowvec, full_height, pol_keep, &s_alloc, zcap,
+                                                     zbuf, jbuf, &pos);
+            if (lane == 0) {
+                s_cnt[r] = count;
+                s_pos[r] = pos;
+                if (pos < 0) atomicAdd(&s_left, 1);
             }
-            int count = 0;
-#pragma unroll
-            for (int k = 0; k < ROUNDS; ++k) {
-                if (full_height) count += (v[k].x != 0.0f) + (v[k].y != 0.0f) + (v[k].z != 0.0f) + (v[k].w != 0.0f);
-                else count += (v[k].x > 0.0f) + (v[k].y > 0.0f) + (v[k].z > 0.0f) + (v[k].w > 0.0f);
-            }
-            count = __reduce_add_sync(0xffffffffu, count);
-            if (lane == 0) s_cnt[r] = count;
         }
         __syncthreads();
         // ---- exclusive scan of the row counts (warp 0), look-back for the grid's base (thread 0) ----
@@ -202,6 +260,7 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
                 if (r < R) s_cnt[r] = run + inc - c;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
+            if (lane == 0) s_cnt[R] = run;
             // decoupled look-back, one warp wide: 32 predecessors per step (lane l looks at grid q - l)
             const unsigned long long total = (unsigned long long)run;
             volatile unsigned long long *stv = status;
@@ -242,59 +301,57 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
             }
         }
         __syncthreads();
-        // ---- pass C: write the points in row-major order (rows come from L2) ----
         const long long gbase = s_base;
-        for (int r = w; r < R; r += K3F_WARPS) {
-            const float4 *row = gp + (size_t)r * rowvec;
-            const double rc = rcs[r];
-            float4 v[ROUNDS];
-#pragma unroll
-            for (int k = 0; k < ROUNDS; ++k) {
-                const int i = k * 32 + lane;
-                v[k] = i < rowvec ? k3_ld(row + i, pol_drop) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            }
-            int64_t base = gbase + s_cnt[r];
-#pragma unroll
-            for (int k = 0; k < ROUNDS; ++k) {
-                const float zc[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-                bool kp[4];
-                unsigned bal[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    kp[c] = full_height ? (zc[c] != 0.0f) : (zc[c] > 0.0f);
-                    bal[c] = __ballot_sync(0xffffffffu, kp[c]);
-                }
-                const int m = __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
-                if (m == 0) continue;
-                // kept cells of lower lanes come first, then this lane's lower components; the round's points are
-                // staged in the warp's shared-memory buffer so that they leave as contiguous 256-byte stores
-                int rank = __popc(bal[0] & lt) + __popc(bal[1] & lt) + __popc(bal[2] & lt) + __popc(bal[3] & lt);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (kp[c]) {
-                        const int j = 4 * (k * 32 + lane) + c;
-                        dbuf[3 * rank + 0] = __dmul_rn(rc, cosT[j]);   // :58  X = r * cos(theta)
-                        dbuf[3 * rank + 1] = __dmul_rn(rc, sinT[j]);   // :59
+        for (;;) {
+            // ---- pass C: expand the compacted rows into points, row-major, 32 points per warp step ----
+            for (int r = w; r < R; r += K3F_WARPS) {
+                const int pos = s_pos[r];
+                if (pos < 0) continue;                       // -1: waits for a later round, -2: already written
+                const int count = s_cnt[r + 1] - s_cnt[r];
+                const double rc = rcs[r];
+                const int64_t obase = gbase + s_cnt[r];
+                for (int e0 = 0; e0 < count; e0 += 32) {
+                    const int m = count - e0 < 32 ? count - e0 : 32;
+                    if (lane < m) {
+                        const float z = zbuf[pos + e0 + lane];
+                        const int j = jbuf[pos + e0 + lane];
+                        dbuf[3 * lane + 0] = __dmul_rn(rc, cosT[j]);   // :58  X = r * cos(theta)
+                        dbuf[3 * lane + 1] = __dmul_rn(rc, sinT[j]);   // :59
                         // :66 the offset is removed in the grid's dtype (float32 .npy grids)
-                        dbuf[3 * rank + 2] = full_height ? (double)zc[c] : (double)__fsub_rn(zc[c], offset_f);
-                        ibuf[rank] = r * S + j;                        // :74
-                        ++rank;
+                        dbuf[3 * lane + 2] = full_height ? (double)z : (double)__fsub_rn(z, offset_f);
+                        ibuf[lane] = r * S + j;                        // :74
                     }
+                    __syncwarp();
+                    for (int t = lane; t < 3 * m; t += 32) {
+                        const int64_t o3 = 3 * (obase + e0) + t;
+                        if (o3 < 3 * cap) __stcs(pts_out + o3, dbuf[t]);
+                    }
+                    if (lane < m && obase + e0 + lane < cap) __stcs(ids_out + obase + e0 + lane, ibuf[lane]);
+                    __syncwarp();
                 }
-                __syncwarp();
-                for (int t = lane; t < 3 * m; t += 32) {
-                    const int64_t o3 = 3 * base + t;
-                    if (o3 < 3 * cap) pts_out[o3] = dbuf[t];
-                }
-                for (int t = lane; t < m; t += 32) {
-                    const int64_t o = base + t;
-                    if (o < cap) ids_out[o] = ibuf[t];
-                }
-                __syncwarp();
-                base += m;
+                if (lane == 0) s_pos[r] = -2;
             }
+            __syncthreads();
+            if (s_left == 0) break;                          // CTA-uniform
+            // ---- a further round for the rows that did not fit: compact them (from L2) into the freed buffer ----
+            __syncthreads();
+            if (tid == 0) {
+                s_alloc = 0;
+                s_left = 0;
+            }
+            __syncthreads();
+            for (int r = w; r < R; r += K3F_WARPS) {
+                if (s_pos[r] != -1) continue;
+                int pos;
+                k3_compact_row<ROUNDS>(gp + (size_t)r * rowvec, rowvec, full_height, pol_drop, &s_alloc, zcap, zbuf, jbuf, &pos);
+                if (lane == 0) {
+                    s_pos[r] = pos;
+                    if (pos < 0) atomicAdd(&s_left, 1);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();                         // s_cnt / s_g are rewritten by the next grid
+        __syncthreads();                         // the row tables and the buffer are rewritten by the next grid
     }
 }
 
@@ -538,11 +595,15 @@ extern "C" int dsc_reconstruct_batch(dsc_ctx *ctx, const float *grids, int n_gri
             DSC_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)n_grids * 8, st));
             const int max_ctas = ctx->sm_count * K3F_CTAS_PER_SM;
             const int ctas = n_grids < max_ctas ? n_grids : max_ctas;   // tickets are drawn by running CTAs only: look-back cannot stall
-            const int k3_smem = K3F_WARPS * K3F_STAGE_BYTES;
+            // shared memory: per-warp staging, the two row tables, and as many compaction entries (6 B) as fit
+            const size_t k3_fixed = (size_t)K3F_WARPS * K3F_STAGE_BYTES + (size_t)(2 * R + 2) * 4 + 16;
+            int zcap = (int)((ctx->smem_optin - 1024 - k3_fixed) / 6) & ~7;
+            if (zcap > R * S) zcap = (R * S + 7) & ~7;
+            const int k3_smem = (int)(k3_fixed + (size_t)zcap * 6);
 #define K3F_LAUNCH(RN)                                                                                          \
     DSC_CUDA(ctx, cudaFuncSetAttribute(k3_fused<RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem));    \
     k3_fused<RN><<<ctas, K3F_THREADS, k3_smem, st>>>(d_grids, n_grids, R, S, full_height, (float)height_offset, ctx->d_rc, \
-                                               ctx->d_cos, ctx->d_sin, ticket, status, item_offsets, d_pts, d_ids, cap)
+                                               ctx->d_cos, ctx->d_sin, ticket, status, item_offsets, d_pts, d_ids, cap, zcap)
             if (rounds <= 2) { K3F_LAUNCH(2); }
             else if (rounds <= 4) { K3F_LAUNCH(4); }
             else if (rounds <= 6) { K3F_LAUNCH(6); }

@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -125,6 +126,7 @@ class Engine:
         self._pid = os.getpid()
         self.device = int(device)
         self._tables_key = None
+        self._pinned = {}
 
     @property
     def _h(self):
@@ -140,6 +142,9 @@ class Engine:
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_handle", None) is not None and self._pid == os.getpid():
+            for addr, fin in list(getattr(self, "_pinned", {}).items()):      # pinned buffers die with the engine
+                fin.detach()
+                self._free_pinned(addr)
             self._lib.dsc_destroy(self._handle)
         self._handle = None
 
@@ -179,16 +184,22 @@ class Engine:
         return float(self._lib.dsc_last_kernel_ms(self._h))
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:
-        """NumPy array over page-locked host memory (freed with the engine)."""
+        """NumPy array over page-locked host memory.  The allocation is released when the array (and every view of
+        it) has been garbage-collected, or when the engine is closed, whichever comes first -- do not touch such an
+        array after ``close()``."""
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
         p = C.c_void_p()
         self._check(self._lib.dsc_host_alloc(self._h, n, C.byref(p)))
         buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        self._pinned = getattr(self, "_pinned", [])
-        self._pinned.append(p)
+        addr = int(p.value)
+        self._pinned[addr] = weakref.finalize(buf, self._free_pinned, addr)     # buf lives as long as arr.base does
         return arr
+
+    def _free_pinned(self, addr: int):
+        if self._pinned.pop(addr, None) is not None and self._handle is not None and self._pid == os.getpid():
+            self._lib.dsc_host_free(self._handle, C.c_void_p(addr))
 
     # -- K1 ------------------------------------------------------------------------------------
     def build_host(self, pts: np.ndarray, offsets: np.ndarray, params: ScanContextParams,

@@ -486,3 +486,23 @@ def test_many_small_scans_with_empty_ones(engine, orc, n_scans):
         ref = orc.sc_build(sc)[0] if len(sc) else np.zeros((160, 720), np.float32)
         assert np.array_equal(got[i], ref), i
         assert int(stats[i][0]) == len(sc)
+
+
+def test_reconstructor_dense_grids_take_several_compaction_rounds(orc):
+    """K3 compacts a grid's kept cells into shared memory (~33 k entries); denser grids are emitted in several rounds.
+    Fully dense, 60 % dense, one dense ring band, and a sparse grid in one batch, both height modes."""
+    from distropointclouds_b200.engine import Engine
+    rng = np.random.default_rng(21)
+    g = np.zeros((5, 160, 720), np.float32)
+    g[0] = rng.standard_normal((160, 720)).astype(np.float32) + 0.01                     # every cell kept
+    g[1] = np.where(rng.random((160, 720)) < 0.6, rng.standard_normal((160, 720)), 0).astype(np.float32)
+    g[2, 40:110] = (rng.standard_normal((70, 720)) * 3).astype(np.float32)              # 50 400 kept cells in a band
+    g[3] = np.where(rng.random((160, 720)) < 0.05, 1.5, 0).astype(np.float32)
+    g[4, ::2, ::3] = -0.25
+    with Engine(0) as e:
+        for full in (True, False):
+            out = e.reconstruct_host(g, full_height=full, height_offset=2.0)
+            for i in range(len(g)):
+                op, oi = orc.reconstruct(g[i], full_height=full, height_offset=2.0)
+                assert np.array_equal(out[i][1], oi), (full, i)
+                assert np.array_equal(out[i][0], op), (full, i)

@@ -157,3 +157,26 @@ def test_oracle_against_live_reference_when_present(orc, golden_scans):
         ref.variant_a(np.array([[np.nan, 1.0, 0.0]], np.float32))
     _, st = orc.sc_build(np.array([[np.nan, 1.0, 0.0]], np.float32))
     assert st["n_nonfinite"] == 1
+
+
+def test_numpy_restatement_reproduces_golden_and_live_reference(orc, golden_scans, golden_grids, ref_live):
+    """oracle/restated.py (the NumPy path bench.py times on the GPU box): variant A with the fdlibm arctan2 plugged in
+    is the golden grid bit for bit; with the host's own arctan2 both variants equal the live-reference fixtures
+    wherever the fixture host's arctan2 flavour agrees with this host's (checked through the C oracle)."""
+    from oracle import restated
+    sid = "002073"
+    pts = golden_scans[sid][:, :3]
+    g = restated.variant_a(pts, arctan2=lambda y, x: orc.atan2f(y, x))
+    assert g.dtype == np.float64 and np.array_equal(g.astype(np.float32), golden_grids[sid])
+    for name in ("a_default", "a_offset", "a_nondyadic"):
+        p, cfg, th = ref_live[f"{name}__pts"], ref_live[f"{name}__cfg"], ref_live[f"{name}__atan2"]
+        got = restated.variant_a(p, np.int64(cfg[1]), np.int64(cfg[0]), int(cfg[2]), bool(cfg[3]), float(cfg[4]),
+                                 arctan2=lambda y, x, th=th: th)
+        assert np.array_equal(got, ref_live[f"{name}__grid"]), name
+    for name in ("b_default", "b_full", "b_nondyadic"):
+        p, cfg, th = ref_live[f"{name}__pts"], ref_live[f"{name}__cfg"], ref_live[f"{name}__atan2"]
+        with np.errstate(invalid="ignore"):
+            fin = np.isfinite(p).all(axis=1)
+            got = restated.variant_b(p.copy(), float(cfg[2]), int(cfg[1]), int(cfg[0]), bool(cfg[3]), float(cfg[4]),
+                                     arctan2=lambda y, x, th=th[fin]: th)
+        assert np.array_equal(got, ref_live[f"{name}__grid"]), name
