@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DSC_LIB") or os.path.join(_HERE, "libdsc.so")     # D
 DSC_OK, DSC_ERR_INVALID, DSC_ERR_CUDA, DSC_ERR_NOMEM, DSC_ERR_CAPACITY = 0, -1, -2, -3, -4
 MEM_HOST, MEM_DEVICE = 0, 1
 VARIANT_A, VARIANT_B = 0, 1
-FLAG_GAP_F32, FLAG_EXACT_ONLY = 1, 2
+FLAG_GAP_F32, FLAG_EXACT_ONLY, FLAG_GAP_RING_F32, FLAG_GAP_SECTOR_F32 = 1, 2, 4, 8
 
 EXPORTS = (
     "dsc_version", "dsc_create", "dsc_destroy", "dsc_last_error", "dsc_set_timing", "dsc_last_kernel_ms",

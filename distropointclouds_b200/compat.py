@@ -17,7 +17,7 @@ from typing import Dict, Iterable, List, Optional, Tuple
 import numpy as np
 
 from . import _ffi
-from .engine import ScanContextParams, default_engine
+from .engine import ScanContextParams, default_engine, variant_a_gap_dtypes
 from .scan_context import _raise_like_reference, _is_np_int
 
 _STATS = _ffi.STATS_FIELDS
@@ -34,7 +34,7 @@ def _ptcloud2sc_vectorized(self, ptcloud, num_sector, num_ring, max_length):
     params = ScanContextParams(
         num_ring=int(num_ring), num_sector=int(num_sector), max_length=float(max_length), variant=_ffi.VARIANT_A,
         full_height=bool(cls.use_full_height_range), height_offset=float(cls.custom_height_offset),
-        gap_f32=not (_is_np_int(num_ring) or _is_np_int(num_sector) or isinstance(max_length, np.floating)))
+        gap_f32=variant_a_gap_dtypes(num_sector, num_ring, max_length))
     grid, stats = default_engine(device).build_any(ptcloud, params)       # float32 (.bin) or float64 (down-sampled)
     cls.last_stats = dict(zip(_STATS, (int(v) for v in stats)))
     if strict:

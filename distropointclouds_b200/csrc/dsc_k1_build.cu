@@ -116,7 +116,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     const int64_t cells = (int64_t)p->num_ring * p->num_sector;
     const BinCfg cfg = dsc::make_bin_cfg(p->num_ring, p->num_sector, p->max_length, p->variant,
                                          p->full_height, p->height_offset,
-                                         (p->flags & DSC_FLAG_GAP_F32) != 0,
+                                         ((p->flags & DSC_FLAG_GAP_F32) ? 3 : 0) | ((p->flags & DSC_FLAG_GAP_RING_F32) ? 1 : 0) |
+                                             ((p->flags & DSC_FLAG_GAP_SECTOR_F32) ? 2 : 0),
                                          (p->flags & DSC_FLAG_EXACT_ONLY) != 0);
     const bool vec16 = stride == 16 && (((uintptr_t)pts) & 15) == 0;
     int rc;

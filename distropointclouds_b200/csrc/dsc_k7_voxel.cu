@@ -229,7 +229,7 @@ extern "C" int dsc_voxel_downsample(dsc_ctx *ctx, const void *pts, int64_t n_poi
     if (!(voxel_size > 0.0) || !isfinite(voxel_size)) DSC_FAIL(ctx, DSC_ERR_INVALID, "voxel_size <= 0");     // Open3D: same error
     if (!n_out) DSC_FAIL(ctx, DSC_ERR_INVALID, "n_out is NULL");
     const int elem = pts_f64 ? 8 : 4;
-    if (pts_stride_bytes < 3 * elem || pts_stride_bytes % elem) DSC_FAIL(ctx, DSC_ERR_INVALID, "bad pts_stride_bytes");
+    if (n_points > 0 && (pts_stride_bytes < 3 * elem || pts_stride_bytes % elem)) DSC_FAIL(ctx, DSC_ERR_INVALID, "bad pts_stride_bytes");
     if (n_points > 0x7fffffffLL) DSC_FAIL(ctx, DSC_ERR_INVALID, "too many points");
     if (mem != DSC_MEM_HOST && mem != DSC_MEM_DEVICE) DSC_FAIL(ctx, DSC_ERR_INVALID, "bad mem");
     if (n_points > 0 && !pts) DSC_FAIL(ctx, DSC_ERR_INVALID, "pts is NULL");

@@ -166,7 +166,7 @@ struct BinCfg {
     int32_t full_height;
     float   offset;       // custom_height_offset as float32
     int32_t pow2;         // both gaps are powers of two: the `//` reduces to an exact scale + floor
-    int32_t gap_f32;      // variant A, non-pow2: float32 floor_divide
+    int32_t gap_f32;      // variant A, non-pow2: float32 floor_divide for the ring gap (bit 0) / the sector gap (bit 1)
     float   inv_gap_ring_f, inv_gap_sector_f;   // exact reciprocals when pow2
     float   gap_ring_f, gap_sector_f;           // float32(gap): variant B divides by these
     double  gap_ring_d, gap_sector_d;
@@ -257,15 +257,11 @@ DSC_HD BinResult bin_exact_a(const BinCfg &c, float x, float y, float z)
         clamped = rf >= (float)c.R;
         ring = rf >= (float)(c.R - 1) ? c.R - 1 : (int)rf;
         sector = (int)fmul(t, c.inv_gap_sector_f);
-    } else if (c.gap_f32) {
-        const float rf = np_floor_dividef(r, c.gap_ring_f);
-        const float sf = np_floor_dividef(t, c.gap_sector_f);
-        clamped = rf > (float)(c.R - 1);
-        ring = rf < (float)(c.R - 1) ? (int)rf : c.R - 1;
-        sector = sf < 2.0e9f ? (int)sf : c.S;
     } else {
-        const double rf = np_floor_divide((double)r, c.gap_ring_d);   // :93, float64
-        const double sf = np_floor_divide((double)t, c.gap_sector_d); // :94
+        // :93-94.  Each `//` runs in the dtype NumPy promotes (float32 array, gap) to: float64 when the gap is an
+        // np.float64 (resolution given as np.int64, the class statics), float32 when it is a Python float (weak scalar).
+        const double rf = (c.gap_f32 & 1) ? (double)np_floor_dividef(r, c.gap_ring_f) : np_floor_divide((double)r, c.gap_ring_d);
+        const double sf = (c.gap_f32 & 2) ? (double)np_floor_dividef(t, c.gap_sector_f) : np_floor_divide((double)t, c.gap_sector_d);
         clamped = rf > (double)(c.R - 1);
         ring = rf < (double)(c.R - 1) ? (int)rf : c.R - 1;
         sector = sf < 2.0e9 ? (int)sf : c.S;

@@ -27,17 +27,34 @@ class ScanContextParams:
     variant: int = _ffi.VARIANT_A
     full_height: bool = True
     height_offset: float = 2.0
-    gap_f32: bool = False       # variant A called with Python-int resolutions
+    gap_f32: object = False     # variant A: which `//` NumPy runs in float32 -- False: none, True / 3: both gaps,
+    #                             1: the ring gap only, 2: the sector gap only (see variant_a_gap_dtypes)
     exact_only: bool = False    # disable the screened fast path
 
     def c(self) -> _ffi.DscParams:
-        flags = (_ffi.FLAG_GAP_F32 if self.gap_f32 else 0) | (_ffi.FLAG_EXACT_ONLY if self.exact_only else 0)
+        g = 3 if self.gap_f32 is True else int(self.gap_f32)
+        flags = ((_ffi.FLAG_GAP_RING_F32 if g & 1 else 0) | (_ffi.FLAG_GAP_SECTOR_F32 if g & 2 else 0) |
+                 (_ffi.FLAG_EXACT_ONLY if self.exact_only else 0))
         return _ffi.DscParams(int(self.num_ring), int(self.num_sector), float(self.max_length),
                               int(self.variant), int(bool(self.full_height)), float(self.height_offset), flags)
 
     @property
     def cells(self) -> int:
         return int(self.num_ring) * int(self.num_sector)
+
+
+def variant_a_gap_dtypes(num_sector, num_ring, max_length) -> int:
+    """Which of variant A's two floor-divides NumPy evaluates in float32 for a float32 cloud (scaner_version2.py:70-71,
+    93-94): ``gap_ring = max_length / num_ring`` and ``gap_sector = 360 / num_sector`` are np.float64 when the resolution
+    (or max_length) is a NumPy scalar -- the class statics are np.int64 -- and the `//` then runs in float64; with plain
+    Python numbers the gap is a weak Python float and the `//` stays float32.  Under NumPy 1.x (value-based casting) a
+    float64 *scalar* does not upcast a float32 array either, so both run in float32.  Returns the gap_f32 mask
+    (bit 0: ring gap, bit 1: sector gap); it only matters for gaps that are not powers of two."""
+    if int(np.__version__.split(".")[0]) < 2:
+        return 3
+    ring64 = isinstance(num_ring, np.generic) or isinstance(max_length, np.generic)
+    sector64 = isinstance(num_sector, np.generic)
+    return (0 if ring64 else 1) | (0 if sector64 else 2)
 
 
 def polar_tables(num_ring: int, num_sector: int, max_length: float):
@@ -423,6 +440,8 @@ class Engine:
         if not p.flags.c_contiguous:
             p = np.ascontiguousarray(p)
         n = p.shape[0]
+        if n == 0:
+            return np.empty((0, 3), np.float64), 0
         out = np.empty((max(n, 1), 3), np.float64)
         n_out, n_drop = C.c_int64(0), C.c_int64(0)
         self._check(self._lib.dsc_voxel_downsample(self._h, _ptr(p), n, int(p.dtype == np.float64), int(p.strides[0]),

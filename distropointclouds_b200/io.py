@@ -86,9 +86,11 @@ def save_pedestrians_json(path: str, pedestrian_info: List[Dict]) -> None:
 
 
 def process_bin_dir(bin_dir: str, out_dir: str, params: ScanContextParams = ScanContextParams(),
-                    device: int = 0, batch_bytes: int = 2 << 30) -> List[str]:
+                    device: int = 0, batch_bytes: int = 2 << 30, strict: bool = True) -> List[str]:
     """The numeric part of scaner_version2.py's __main__ + process_dataset_to_images (:430-487, :372-427) for a
-    whole directory: every .bin -> sc_<stem>.npy, in batches of at most `batch_bytes` of points."""
+    whole directory: every .bin -> sc_<stem>.npy, in batches of at most `batch_bytes` of points.
+    strict: raise IndexError (naming the file) where the reference's variant A would -- NaN / Inf coordinates or an
+    angle that rounds to 360.0 (its own sample_data/999999.bin does); strict=False drops such points silently."""
     eng = default_engine(device)
     names = list_bin_files(bin_dir)
     written: List[str] = []
@@ -99,7 +101,13 @@ def process_bin_dir(bin_dir: str, out_dir: str, params: ScanContextParams = Scan
             tot += os.path.getsize(os.path.join(bin_dir, names[j]))
             j += 1
         pts, offs = read_bin_batch([os.path.join(bin_dir, n) for n in names[i:j]])
-        grids, _, _ = eng.build_host(pts, offs, params, 16, want_stats=False)
+        grids, _, stats = eng.build_host(pts, offs, params, 16, want_stats=strict)
+        if strict and params.variant == 0:
+            bad = np.flatnonzero((stats[:, 1] + stats[:, 2]) > 0)
+            if bad.size:
+                k = int(bad[0])
+                raise IndexError(f"{names[i + k]}: {int(stats[k, 1])} point(s) with non-finite polar coordinates, "
+                                 f"{int(stats[k, 2])} whose angle rounds to 360.0 (the reference raises IndexError here)")
         written += save_sc_batch(out_dir, [n.split(".")[0] for n in names[i:j]], grids)
         i = j
     return written

@@ -21,7 +21,7 @@ from typing import Optional
 import numpy as np
 
 from . import _ffi
-from .engine import Engine, ScanContextParams, default_engine, pack_scans
+from .engine import Engine, ScanContextParams, default_engine, pack_scans, variant_a_gap_dtypes
 from . import labels as _labels
 
 _STATS = _ffi.STATS_FIELDS
@@ -97,7 +97,7 @@ class ScanContext:
             height_offset=float(cls.custom_height_offset),
             # np.int64 resolutions (the class statics) make the gaps np.float64 -> float64 `//`;
             # Python ints make them weak scalars -> float32 `//`   (scaner_version2.py:70-71,93-94)
-            gap_f32=not (_is_np_int(num_ring) or _is_np_int(num_sector) or isinstance(max_length, np.floating)),
+            gap_f32=variant_a_gap_dtypes(num_sector, num_ring, max_length),
         )
         grid, stats = cls._engine().build_any(ptcloud, params)
         ScanContext.last_stats = dict(zip(_STATS, (int(v) for v in stats)))

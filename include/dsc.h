@@ -56,7 +56,9 @@ enum { DSC_VARIANT_A = 0, DSC_VARIANT_B = 1 };
 enum {
     DSC_FLAG_GAP_F32 = 1,    /* variant A: num_ring/num_sector were Python ints, so NumPy does the
                                 `//` in float32 instead of float64 (matters for non-dyadic gaps) */
-    DSC_FLAG_EXACT_ONLY = 2  /* disable the screened fast path; every point takes the fdlibm path */
+    DSC_FLAG_EXACT_ONLY = 2, /* disable the screened fast path; every point takes the fdlibm path */
+    DSC_FLAG_GAP_RING_F32 = 4,   /* as DSC_FLAG_GAP_F32, for the ring gap only (max_length / num_ring a Python float) */
+    DSC_FLAG_GAP_SECTOR_F32 = 8  /* ... for the sector gap only (360 / num_sector a Python float) */
 };
 
 /* The reference keeps these as class statics (scaner_version2.py:28-47, kitti_dataset.py:28-41,

@@ -18,7 +18,7 @@ typedef struct {
     int32_t variant;       /* ORC_VARIANT_A: scaner_version2.py:64-115; _B: scan_context_node.py:102-157 */
     int32_t full_height;   /* use_full_height_range */
     float   height_offset; /* custom_height_offset (float32 add) */
-    int32_t gap_f32;       /* variant A only: 1 when num_ring/num_sector were Python ints (f32 `//`) */
+    int32_t gap_f32;       /* variant A only: which `//` runs in float32 (Python-int resolution): bit 0 ring gap, bit 1 sector gap */
 } orc_params;
 
 typedef struct {

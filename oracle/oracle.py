@@ -122,7 +122,7 @@ class Params:
     def c(self) -> OrcParams:
         return OrcParams(int(self.num_ring), int(self.num_sector), float(self.max_length),
                          int(self.variant), int(bool(self.full_height)), float(self.height_offset),
-                         int(bool(self.gap_f32)))
+                         3 if self.gap_f32 is True else int(self.gap_f32))       # True: both gaps; 1: ring only; 2: sector only
 
 
 def atan2f(y, x) -> np.ndarray:

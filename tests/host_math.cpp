@@ -11,7 +11,7 @@ float hm_atan2f(float y, float x) { return dsc::atan2f_fdlibm(y, x); }
 void hm_bin_exact(int R, int S, double max_length, int variant, int full_height, float offset, int gap_f32,
                   const float *xyz, long long n, int stride_floats, int *cell, int *status, float *z)
 {
-    const dsc::BinCfg c = dsc::make_bin_cfg(R, S, max_length, variant, full_height, offset, gap_f32, 1);
+    const dsc::BinCfg c = dsc::make_bin_cfg(R, S, max_length, variant, full_height, offset, gap_f32 == 1 ? 3 : gap_f32, 1);  // 1: both gaps, 4|1: ring only, 2: sector only
     for (long long i = 0; i < n; ++i) {
         const float *p = xyz + i * stride_floats;
         const dsc::BinResult b = dsc::bin_exact(c, p[0], p[1], p[2]);

@@ -75,8 +75,13 @@ def test_live_computer(tmp_path, golden_scans, orc):
     comp = ScanContextComputer(output_dir=str(tmp_path / "o"), dl_images_dir=str(tmp_path / "i"))
     pts = np.ascontiguousarray(golden_scans["002073"][:, :3])
     sc, _, npy = comp.compute_and_save(pts, "000001")
-    o, _ = orc.sc_build(pts, orc.Params(max_length=80.0, variant=orc.VARIANT_B, full_height=False))
+    # compute_and_save = voxel down-sample (float64 voxel means) -> float64 variant B  (scan_context_node.py:159-168)
+    ds, _ = orc.voxel_downsample(pts, comp.voxel_size)
+    o, _ = orc.sc_build_f64(ds, orc.Params(max_length=80.0, variant=orc.VARIANT_B, full_height=False))
     assert sc.dtype == np.float32 and np.array_equal(sc, o) and np.array_equal(np.load(npy), o)
+    # the bare generator on the raw float32 cloud is the float32 chain
+    o32, _ = orc.sc_build(pts, orc.Params(max_length=80.0, variant=orc.VARIANT_B, full_height=False))
+    assert np.array_equal(comp._scan_context(pts), o32)
     assert not comp._scan_context(np.zeros((0, 3), np.float32)).any()
 
 

@@ -33,8 +33,19 @@ def test_pack_scans_ragged_and_empty():
 
 
 def test_params_struct():
+    from distropointclouds_b200 import _ffi
+    from distropointclouds_b200.engine import variant_a_gap_dtypes
     p = ScanContextParams(gap_f32=True, exact_only=True).c()
-    assert p.flags == 3 and p.num_ring == 160 and p.max_length == 20.0
+    assert p.flags == (_ffi.FLAG_GAP_RING_F32 | _ffi.FLAG_GAP_SECTOR_F32 | _ffi.FLAG_EXACT_ONLY)
+    assert p.num_ring == 160 and p.max_length == 20.0
+    assert ScanContextParams(gap_f32=2).c().flags == _ffi.FLAG_GAP_SECTOR_F32
+    # scaner_version2.py:70-71: np.int64 resolutions (the class statics) make the gaps np.float64 -> float64 `//`;
+    # Python ints make them weak Python floats -> float32 `//`; the two gaps are derived independently (NumPy >= 2)
+    assert variant_a_gap_dtypes(np.int64(720), np.int64(160), 20) == 0
+    assert variant_a_gap_dtypes(720, 160, 20) == 3
+    assert variant_a_gap_dtypes(720, np.int64(160), 20) == 2
+    assert variant_a_gap_dtypes(np.int64(720), 160, 20) == 1
+    assert variant_a_gap_dtypes(np.int64(720), 160, np.float64(20.0)) == 0
 
 
 def test_polar_tables_are_the_reference_expressions():

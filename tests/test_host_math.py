@@ -210,3 +210,23 @@ def test_random_bit_patterns(hm, orc):
             assert (st == 4).sum() == stt["n_out_of_range"] and (st == 1).sum() == stt["n_clamped_ring"]
             bad, _ = _check_fast(hm, pts, var=var, full=full, noise_mode="rand")
             assert bad == 0
+
+
+def test_mixed_gap_dtypes_follow_numpy(hm, orc):
+    """Non-dyadic gaps with only ONE of the two resolutions given as np.int64: the two floor-divides run in
+    different dtypes.  The device code (host build) == the oracle == NumPy itself, point by point."""
+    rng = np.random.default_rng(12)
+    pts = (rng.standard_normal((20000, 3)) * [12, 12, 1]).astype(np.float32)
+    pts[:, 0] = np.where(pts[:, 0] == 0, 0.001, pts[:, 0]); pts[:, 1] = np.where(pts[:, 1] == 0, 0.001, pts[:, 1])
+    R, S, ml = 150, 700, 33
+    th = np.rad2deg(orc.atan2f(pts[:, 1], pts[:, 0])) % 360
+    r = np.sqrt(pts[:, 0] * pts[:, 0] + pts[:, 1] * pts[:, 1])
+    for mask, nr, ns in ((2, np.int64(R), S), (1, R, np.int64(S))):
+        ring = np.minimum(r // (ml / nr), R - 1).astype(np.int32)          # NumPy's own promotion decides
+        sec = (th // (360 / ns)).astype(np.int32)
+        cell, st, _ = bin_exact(hm, pts, R, S, float(ml), 0, 1, 2.0, 5 if mask == 1 else 2)   # 5 -> (4|1) is not 1: ring only
+        ok = st <= 1
+        assert np.array_equal(cell[ok], (ring * S + sec)[ok]), mask
+        o, _ = orc.sc_build(pts, orc.Params(R, S, float(ml), 0, True, 2.0, mask))
+        g = grid_from(cell, st, pts[:, 2].copy(), R, S, True)
+        assert np.array_equal(g, o), mask
