@@ -132,7 +132,7 @@ constexpr int K3F_CTAS_PER_SM = 1;
 constexpr int K3F_WARPS = K3F_THREADS / 32;
 constexpr int K3F_MAXR = 2048;                                 // rows per grid the shared-memory scan can hold
 constexpr int K3F_MAXROUNDS = 8;                               // 128 cells per warp round: S <= 1024 (sector fits 16 bits)
-constexpr int K3F_STAGE_BYTES = 32 * 24 + 32 * 4;              // per-warp output staging: 32 points
+constexpr int K3F_STAGE_BYTES = 32 * 24;                       // per-warp output staging: 32 points x 3 doubles
 constexpr unsigned long long K3F_AGG = 1ull << 62, K3F_PFX = 2ull << 62, K3F_VAL = (1ull << 62) - 1;
 
 // One ring row per warp at a time, read as 128-bit vectors with every load of the row in flight at once
@@ -207,13 +207,13 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
          int64_t *__restrict__ item_offsets, double *__restrict__ pts_out, int32_t *__restrict__ ids_out, int64_t cap,
          const int zcap)
 {
-    __shared__ int s_g, s_alloc, s_left;
+    __shared__ int s_g, s_alloc, s_left, s_rowA, s_rowC;
+    __shared__ volatile int s_ready;             // the grid's base offset has been published (look-back done)
     __shared__ long long s_base;
     // dynamic: [per-warp staging][row offsets R+1][row buffer positions R][heights zcap][sectors zcap]
     extern __shared__ __align__(16) double k3_smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double *dbuf = k3_smem + (size_t)w * (K3F_STAGE_BYTES / 8);
-    int *ibuf = reinterpret_cast<int *>(dbuf + 96);
     int *s_cnt = reinterpret_cast<int *>(k3_smem + (size_t)K3F_WARPS * (K3F_STAGE_BYTES / 8));
     int *s_pos = s_cnt + (R + 1);
     float *zbuf = reinterpret_cast<float *>(s_pos + R + ((R + 1 + R) & 1));
@@ -228,13 +228,20 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
             s_g = (int)atomicAdd(ticket, 1u);
             s_alloc = 0;
             s_left = 0;
+            s_rowA = 0;
+            s_rowC = 0;
+            s_ready = 0;
         }
         __syncthreads();
         const int g = s_g;
         if (g >= n_grids) break;
         const float4 *gp = reinterpret_cast<const float4 *>(grids + (size_t)g * R * S);
-        // ---- pass A: count + compact every row ----
-        for (int r = w; r < R; r += K3F_WARPS) {
+        // ---- pass A: count + compact every row; rows are handed out dynamically (dense rows take longer) ----
+        for (;;) {
+            int r = 0;
+            if (lane == 0) r = atomicAdd(&s_rowA, 1);
+            r = __shfl_sync(0xffffffffu, r, 0);
+            if (r >= R) break;
             int pos;
             const int count = k3_compact_row<ROUNDS>(gp + (size_t)r * rowvec, rowvec, full_height, pol_keep, &s_alloc, zcap,
                                                      zbuf, jbuf, &pos);
@@ -245,9 +252,9 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
             }
         }
         __syncthreads();
-        // ---- exclusive scan of the row counts (warp 0), look-back for the grid's base (thread 0) ----
+        // ---- exclusive scan of the row counts (warp 0) ----
+        int run = 0;
         if (w == 0) {
-            int run = 0;
             for (int r0 = 0; r0 < R; r0 += 32) {
                 const int r = r0 + lane;
                 const int c = r < R ? s_cnt[r] : 0;
@@ -261,7 +268,11 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
             if (lane == 0) s_cnt[R] = run;
-            // decoupled look-back, one warp wide: 32 predecessors per step (lane l looks at grid q - l)
+        }
+        __syncthreads();
+        // ---- warp 0: decoupled look-back for the grid's base offset, 32 predecessors per step (lane l looks at grid
+        //      q - l).  The other warps already expand rows (pass C) and only wait for the base before their first store.
+        if (w == 0) {
             const unsigned long long total = (unsigned long long)run;
             volatile unsigned long long *stv = status;
             long long base = 0;
@@ -298,35 +309,63 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
                 item_offsets[g] = base;
                 if (g == n_grids - 1) item_offsets[n_grids] = base + (long long)total;
                 s_base = base;
+                __threadfence_block();
+                s_ready = 1;
             }
         }
-        __syncthreads();
-        const long long gbase = s_base;
+        bool have_base = false;
+        long long gbase = 0;
         for (;;) {
             // ---- pass C: expand the compacted rows into points, row-major, 32 points per warp step ----
-            for (int r = w; r < R; r += K3F_WARPS) {
+            for (;;) {
+                int r = 0;
+                if (lane == 0) r = atomicAdd(&s_rowC, 1);
+                r = __shfl_sync(0xffffffffu, r, 0);
+                if (r >= R) break;
                 const int pos = s_pos[r];
                 if (pos < 0) continue;                       // -1: waits for a later round, -2: already written
-                const int count = s_cnt[r + 1] - s_cnt[r];
+                const int rowoff = s_cnt[r];
+                const int count = s_cnt[r + 1] - rowoff;
+                if (count == 0) continue;
                 const double rc = rcs[r];
-                const int64_t obase = gbase + s_cnt[r];
-                for (int e0 = 0; e0 < count; e0 += 32) {
-                    const int m = count - e0 < 32 ? count - e0 : 32;
+                const int idbase = r * S;
+                if (!have_base) {                            // first store of this warp for this grid
+                    while (!s_ready) __nanosleep(20);
+                    __threadfence_block();
+                    gbase = s_base;
+                    have_base = true;
+                }
+                // 32 points per step: each lane expands one compacted entry into its staging slot, then the warp
+                // copies the 768 contiguous bytes out with three fully coalesced 8-byte stores per lane
+                const int64_t obase = gbase + rowoff;
+                double *dst = pts_out + 3 * obase + lane;
+                int32_t *idst = ids_out + obase + lane;
+                const bool fits = obase + count <= cap;      // (capacity overflow is reported by the host wrapper)
+                const float *zp = zbuf + pos + lane;
+                const unsigned short *jp = jbuf + pos + lane;
+                for (int e0 = 0; e0 < count; e0 += 32, dst += 96, idst += 32) {
+                    const int m = count - e0;                // >= 32 except in the row's last step
+                    int id = 0;
                     if (lane < m) {
-                        const float z = zbuf[pos + e0 + lane];
-                        const int j = jbuf[pos + e0 + lane];
+                        const float z = zp[e0];
+                        const int j = jp[e0];
                         dbuf[3 * lane + 0] = __dmul_rn(rc, cosT[j]);   // :58  X = r * cos(theta)
                         dbuf[3 * lane + 1] = __dmul_rn(rc, sinT[j]);   // :59
                         // :66 the offset is removed in the grid's dtype (float32 .npy grids)
                         dbuf[3 * lane + 2] = full_height ? (double)z : (double)__fsub_rn(z, offset_f);
-                        ibuf[lane] = r * S + j;                        // :74
+                        id = idbase + j;                               // :74
                     }
                     __syncwarp();
-                    for (int t = lane; t < 3 * m; t += 32) {
-                        const int64_t o3 = 3 * (obase + e0) + t;
-                        if (o3 < 3 * cap) __stcs(pts_out + o3, dbuf[t]);
+                    if (m >= 32 && fits) {
+                        __stcs(dst, dbuf[lane]);
+                        __stcs(dst + 32, dbuf[lane + 32]);
+                        __stcs(dst + 64, dbuf[lane + 64]);
+                        __stcs(idst, id);
+                    } else {
+                        for (int t = lane; t < 3 * m && t < 96; t += 32)
+                            if (3 * (obase + e0) + t < 3 * cap) __stcs(dst + (t - lane), dbuf[t]);
+                        if (lane < m && obase + e0 + lane < cap) __stcs(idst, id);
                     }
-                    if (lane < m && obase + e0 + lane < cap) __stcs(ids_out + obase + e0 + lane, ibuf[lane]);
                     __syncwarp();
                 }
                 if (lane == 0) s_pos[r] = -2;
@@ -338,6 +377,7 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
             if (tid == 0) {
                 s_alloc = 0;
                 s_left = 0;
+                s_rowC = 0;
             }
             __syncthreads();
             for (int r = w; r < R; r += K3F_WARPS) {

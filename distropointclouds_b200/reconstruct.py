@@ -48,22 +48,20 @@ class ScanContextReconstructor:
         colors = np.full((pts.shape[0], 3), 0.7, dtype=float)
         return pts, colors, ids
 
-    # -- reconstruct_pointcloud.py:81-102 (host I/O, unchanged semantics) ---------------------------
+    # -- reconstruct_pointcloud.py:81-102: the union of every pedestrian's covered_cells list ------
     def load_covered_cells_from_json(self, json_path):
+        """All [ring, sector] pairs of a pedestrians_*.json, in file order (duplicates kept: every pedestrian is
+        listed twice upstream).  A missing or malformed file yields an empty list, as in the reference."""
+        if not os.path.isfile(json_path):
+            return []
         try:
-            with open(json_path, 'r') as f:
-                peds = json.load(f)
-            covered_cells = []
-            if isinstance(peds, list):
-                for ped in peds:
-                    covered_cells.extend(ped.get('covered_cells', []))
-            return covered_cells
-        except FileNotFoundError:
-            print(f"[WARN] Pedestrian JSON not found: {json_path}")
+            with open(json_path) as f:
+                records = json.load(f)
+        except (OSError, ValueError):
             return []
-        except Exception as e:   # noqa: BLE001 -- the reference swallows everything here too
-            print(f"[WARN] Failed to load JSON {json_path}: {e}")
+        if not isinstance(records, list):
             return []
+        return [cell for rec in records if isinstance(rec, dict) for cell in rec.get('covered_cells', [])]
 
     # -- reconstruct_pointcloud.py:104-130 ----------------------------------------------------------
     def add_covered_cells_to_pointcloud(self, sc_data, covered_cells):

@@ -122,3 +122,29 @@ def test_reconstructor_class(tmp_path, golden_grids, golden_peds, ref_live):
     assert np.array_equal(gp, ref_live["covered_000840__gather_pts"]) and (gc == [1.0, 0.0, 0.0]).all()
     m = build_mask_from_json(160, 720, os.path.join(GOLDEN, "pedestrians_002160.json"))
     assert m.dtype == np.uint8 and np.array_equal(m, ref_live["mask_002160"])
+
+
+@pytest.mark.gpu
+def test_add_covered_cells_offset_mode(golden_grids, golden_peds):
+    """reconstruct_pointcloud.py:104-130 with use_full_height_range = 0: only cells with z > 0 are kept and the height
+    offset is removed in the grid's dtype (float32), against the reference's own NumPy expressions; out-of-grid cell
+    indices are clipped (:109-110)."""
+    from distropointclouds_b200.reconstruct import ScanContextReconstructor
+    sc = (golden_grids["002095"] + np.float32(2.0)) * (golden_grids["002095"] != 0)     # an offset-mode grid (z + 2, empty = 0)
+    sc = sc.astype(np.float32)
+    cov = [c for p in golden_peds["002095"] for c in p["covered_cells"]] + [[-3, 10], [200, 800], [159, 719], [0, 0]]
+
+    class Rec(ScanContextReconstructor):
+        use_full_height_range = 0
+        custom_height_offset = 2.0
+    gp, gc = Rec().add_covered_cells_to_pointcloud(sc, cov)
+    idx = np.array(cov, dtype=int)
+    idx[:, 0] = np.clip(idx[:, 0], 0, 159); idx[:, 1] = np.clip(idx[:, 1], 0, 719)
+    r = (idx[:, 0] + 0.5) * (20 / 160)
+    th = np.deg2rad((idx[:, 1] + 0.5) * (360.0 / 720))
+    x, y, z = r * np.cos(th), r * np.sin(th), sc[idx[:, 0], idx[:, 1]]
+    valid = z > 0
+    ref = np.column_stack((x[valid], y[valid], z[valid] - 2.0))
+    assert gp.dtype == np.float64 and gp.shape == ref.shape and np.array_equal(gp, ref)
+    assert gc.shape == ref.shape and np.all(gc == [1.0, 0.0, 0.0])
+    assert 0 < valid.sum() < len(cov)
