@@ -152,16 +152,30 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     // launch shape (threads x 128-bit loads per thread per register set); shapes other than 0 exist for the
     // screened default-grid kernels only.  Fewer threads = more registers per thread (no spills), fewer warps.
     int shape = (cfg.fast_ok && defgrid) ? ctx->sc_cfg : 2;                     // the generic kernels are 1024 x 2
+#ifdef SC_EXTRA_SHAPES                            // A/B builds: 640 x 3 (102 registers), 512 x 4 (128), 512 x 3
+    if (shape < 0 || shape > 7) shape = 0;
+    const int nthreads = shape == 0 ? 768 : shape == 3 ? 640 : shape == 6 ? 896 : shape == 7 ? 832 : shape >= 4 ? 512 : 1024;
+#else
     if (shape != 1 && shape != 2) shape = 0;
     const int nthreads = shape == 0 ? 768 : 1024;
+#endif
     const size_t row_bytes = (size_t)p->num_sector * 4;
     const size_t q_bytes = cfg.fast_ok ? (size_t)SCQ_WARP_BYTES * (nthreads / 32) : 0;       // per-warp exact-path queues
     // Resident rows.  Shared memory and L1 share 256 KB per SM; beyond the 196 KB carve-out step (164 KB for the
     // 1024-thread shapes) the streaming loads starve (profiles/r1_notes.md: 60 rows 1.99 ms, 64 rows 2.14 ms).
     // Split items have no second pass -- every non-resident point is a RED.MAX on a grid that 16 CTAs share --
     // and want every row they can get (dense2m: 62 rows 0.62 ms, 72 rows 0.53 ms).
+#if SC_ASYNC
+    // the stream is staged through shared memory (SC_NG groups of one point per thread) and no longer lands in L1:
+    // rows + queues + staging may take everything the SM offers
+    const size_t stg_bytes = (size_t)SC_NG * nthreads * 16;
+    const size_t sc_budget = ctx->smem_optin - 1024 - q_bytes - stg_bytes;
+    const size_t sc_max = sc_budget;
+#else
+    const size_t stg_bytes = 0;
     const size_t sc_budget = split ? ctx->smem_optin : (size_t)(nthreads < 1024 ? 196 : 164) * 1024 - 1024 - 256 - q_bytes;
     const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
+#endif
     int ns = (int)((sc_budget < sc_max ? sc_budget : sc_max) / row_bytes);
     if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                          // A/B override
     if ((size_t)ns * row_bytes > sc_max) ns = (int)(sc_max / row_bytes);
@@ -169,7 +183,9 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     // whole scans reduce the rings beyond the resident ones in bands of ns rows, re-reading the spill list once
     // per band: grids with very many rings for their row size go to the generic path instead
     const int bands = ns >= 2 ? (p->num_ring - ns + ns - 1) / ns : 0x7fffffff;
-    const bool sc_ok = sc_shape_ok && ns >= 2 && (split || bands <= 8) &&
+    // (whole-scan items address their spill lists with 32-bit entry indices: sm_count regions of max_pts entries)
+    const bool spill_ok = (int64_t)ctx->sm_count * (max_pts + nthreads) < 0xffff0000LL;
+    const bool sc_ok = sc_shape_ok && ns >= 2 && (split || (bands <= 8 && spill_ok)) &&
                        (split || ctx->k1_impl == 3 || n_scans >= ctx->sm_count / 2);
     if (sc_ok) {
         int ctas = ctx->sm_count;
@@ -240,7 +256,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         }
         unsigned long long *stp = (unsigned long long *)stats;
         const bool full = p->full_height != 0;
-        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
+        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes + stg_bytes;
 #define SC_LAUNCH5(F, V, H, U, NT, D, SP, ST)                                                                   \
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP, ST>,                                  \
@@ -257,10 +273,21 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     do {                                                                                                        \
         if (split) SC_LAUNCH4(F, V, H, U, NT, D, true); else SC_LAUNCH4(F, V, H, U, NT, D, false);              \
     } while (0)
+#ifdef SC_EXTRA_SHAPES
+#define SC_EXTRA_LAUNCH(V, H)                                                                                   \
+        else if (shape == 3) SC_LAUNCH3(true, V, H, 3, 640, true);                                              \
+        else if (shape == 4) SC_LAUNCH3(true, V, H, 4, 512, true);                                              \
+        else if (shape == 5) SC_LAUNCH3(true, V, H, 3, 512, true);                                              \
+        else if (shape == 6) SC_LAUNCH3(true, V, H, 3, 896, true);                                              \
+        else if (shape == 7) SC_LAUNCH3(true, V, H, 3, 832, true);
+#else
+#define SC_EXTRA_LAUNCH(V, H)
+#endif
 #define SC_LAUNCH_DEF(V, H)                                                                                     \
     do {                                                                                                        \
         if (shape == 1) SC_LAUNCH3(true, V, H, 3, 1024, true);                                                  \
         else if (shape == 2) SC_LAUNCH3(true, V, H, 2, 1024, true);                                             \
+        SC_EXTRA_LAUNCH(V, H)                                                                                   \
         else SC_LAUNCH3(true, V, H, 3, 768, true);                                                              \
     } while (0)
         if (cfg.fast_ok && defgrid) {

@@ -29,6 +29,21 @@ constexpr int SC_THREADS = 1024;
 #ifndef SC_SLOT
 #define SC_SLOT 0                     // 1 (A/B builds): whole-scan items reduce the non-resident rings with RED.MAX on a private
 #endif                                // L2 key slot per CTA and read it back (the round-1 form) instead of spill lists + bands
+#ifndef SC_BATCH
+#define SC_BATCH 0                    // 1 (A/B builds): screen the U points of a register set first, then commit them (slower: r2k)
+#endif
+#ifndef SC_NO_PRECHECK
+#define SC_NO_PRECHECK 0
+#endif
+#ifndef SC_ASYNC
+#define SC_ASYNC 0                    // 1: the stream is staged through shared memory with cp.async (see k1_scan)
+#endif
+#ifndef SC_NG
+#define SC_NG 4                       // SC_ASYNC: groups in the staging ring (SC_NG - 1 in flight)
+#endif
+#ifndef SC_VOTE_POINT
+#define SC_VOTE_POINT 1               // 1: one screen-failure vote per point; 0: one per register set
+#endif
 #ifndef SC_LU
 #define SC_LU 4                       // 128-bit spill-list loads in flight per lane in pass 2
 #endif
@@ -52,7 +67,10 @@ struct SplitArgs {
 // whole spends a quarter of its issue slots there with one or two lanes active.  Instead every warp parks such
 // points in a small shared-memory queue (x[64], y[64], z[64]) and runs the exact chain only when 32 are
 // waiting -- all lanes busy -- or when the work item ends.
-constexpr int SCQ_CAP = 64;                                   // entries per warp
+#ifndef SC_QCAP
+#define SC_QCAP 64
+#endif
+constexpr int SCQ_CAP = SC_QCAP;                              // entries per warp (>= 32; below 64 a batch may run part-filled)
 constexpr int SCQ_WARP_BYTES = SCQ_CAP * 12;                  // 768 B per warp
 
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v)
@@ -83,6 +101,21 @@ __device__ __forceinline__ uint4 ld_spill2(const uint2 *p)
     return v;
 }
 
+// 16-byte asynchronous copy global -> shared, past L1 and past the register file (LDGSTS.BYPASS), L2 evict-first
+__device__ __forceinline__ void cp_async16(const uint32_t dst, const void *src, const uint64_t pol)
+{
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds_f4(const uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // max-reduce `key` into the shared-memory cell at `addr` when `doit`: LDS pre-check (most points are not a new maximum)
 // + ATOMS.MAX, predicated instead of branched.
 // `w` is the point's intensity word -- dead data, but it doubles as the destination of the LDS: that keeps its register
@@ -91,6 +124,13 @@ __device__ __forceinline__ uint4 ld_spill2(const uint2 *p)
 // the long scoreboard: one POPC held 20 % of all stall samples in profiles/r2d) and defeats the register ping-pong.
 __device__ __forceinline__ void smem_max_if(const uint32_t addr, const uint32_t key, const bool doit, uint32_t w)
 {
+#if SC_NO_PRECHECK                               // (A/B builds: the atomic alone)
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "setp.ne.u32 p, %3, 0;\n"
+                 "@p red.shared.max.u32 [%1], %2;\n"
+                 "}" : "+r"(w) : "r"(addr), "r"(key), "r"((uint32_t)doit) : "memory");
+#else
     asm volatile("{\n"
                  ".reg .pred p, q;\n"
                  "setp.ne.u32 p, %3, 0;\n"
@@ -98,6 +138,7 @@ __device__ __forceinline__ void smem_max_if(const uint32_t addr, const uint32_t 
                  "setp.gt.and.u32 q, %2, %0, p;\n"
                  "@q red.shared.max.u32 [%1], %2;\n"
                  "}" : "+r"(w) : "r"(addr), "r"(key), "r"((uint32_t)doit) : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint32_t sc_tok3(const float a, const float b, const float c)
@@ -113,19 +154,32 @@ __device__ __forceinline__ uint32_t sc_tok2(const float a, const float b)
     return t;
 }
 
-// Fold one binned point into the key grid.  Called warp-uniformly; `valid` masks lanes without a point.
-//   resident cell      LDS pre-check + ATOMS.MAX
-//   any other cell     SPILL: appended to the warp's spill list (`gbase` = this CTA's list region, `goff` = the warp's
-//                      write position in it, in entries, advanced for the whole warp; `lt` = %lanemask_lt);
-//                      !SPILL (split items): RED.MAX straight into the scan's key grid (`gbase`)
-template <bool FULL, bool SPILL>
-__device__ __forceinline__ void sc_commit(const float zv, const int cell, bool valid, const SmemRows sm, uint32_t *const gbase, uint32_t &goff,
-                                          const unsigned lt, const uint32_t w = 0u)
+// What the key grid holds for a height.  Full-height mode: the order-preserving key (negative heights count, 0 == empty
+// == below everything).  Offset mode: only heights > 0 ever count (strict '>' against cells that start at 0), and for
+// positive floats the raw bit pattern already orders like the value -- the "key" is the float itself, 0 == empty ==
+// 0.0f, and neither the points nor the 115 200 cells written out per scan need a conversion.
+template <bool FULL>
+__device__ __forceinline__ uint32_t sc_key(const float zv)
 {
     const uint32_t u = __float_as_uint(zv);
-    const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);     // order-preserving key
-    valid = valid && (zv == zv);                 // NaN never wins (scaner_version2.py:107)
-    if (!FULL) valid = valid && (zv > 0.0f);     // offset mode: cells start at 0, strict '>'
+    return FULL ? (u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u)) : u;
+}
+// a height takes part in the max: never a NaN (scaner_version2.py:107); offset mode: cells start at 0, strict '>'
+template <bool FULL>
+__device__ __forceinline__ bool sc_counts(const float zv)
+{
+    return FULL ? (zv == zv) : (zv > 0.0f);
+}
+
+// Fold one binned point into the key grid.  Called warp-uniformly; `valid` masks lanes without a (counting) point.
+//   resident cell      LDS pre-check + ATOMS.MAX
+//   any other cell     SPILL: appended to the warp's spill list (`gbase` = the launch's spill buffer, `goff` = the warp's
+//                      write position in it, in entries, advanced for the whole warp; `lt` = %lanemask_lt);
+//                      !SPILL (split items): RED.MAX straight into the scan's key grid (`gbase`)
+template <bool SPILL>
+__device__ __forceinline__ void sc_commit(const uint32_t key, const int cell, const bool valid, const SmemRows sm, uint32_t *const gbase,
+                                          uint32_t &goff, const unsigned lt, const uint32_t w = 0u)
+{
     const int rel = cell - sm.c0;
     const bool win = (uint32_t)rel < (uint32_t)sm.lim;                          // rings r0 .. r0+ns-2
     const bool res = win || cell >= sm.last;
@@ -174,48 +228,104 @@ __device__ __forceinline__ void sc_exact_batch(const uint32_t queue, const unsig
     __syncwarp();
     const int status = (int)(b.x >> 27);
     n_clamped += (mine && status == dsc::PT_CLAMPED) ? 1u : 0u;
-    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED, sm, gbase, goff, lt);
+    const float zv = __uint_as_float(b.y);
+    sc_commit<SPILL>(sc_key<FULL>(zv), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED && sc_counts<FULL>(zv), sm, gbase, goff, lt);
 }
 
-// One point per lane, called warp-uniformly (`active` masks lanes past the end of the item).
+// Park the points that failed the screen (`slow` lanes) in the warp's exact-path queue; run the exact chain when 32 wait.
+// Called warp-uniformly, on the rare path only.
+template <int VARIANT, bool FULL, bool SPILL, bool STATS>
+__device__ __forceinline__ void sc_park(const ExactArgs *ea, const float4 v, const bool slow, uint32_t *const gbase, uint32_t &goff,
+                                        unsigned &n_clamped, unsigned long long *__restrict__ stats, const int scan,
+                                        const SmemRows sm, const uint32_t qoff, unsigned &qcount, const unsigned lt)
+{
+    // (the thread index is read here, opaquely, so that the queue address is formed on this path instead of being
+    // hoisted out of the streaming loop into a register of its own)
+    unsigned t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    const uint32_t queue = sm.base + qoff + (t >> 5) * SCQ_WARP_BYTES;
+    const unsigned m = __ballot_sync(0xffffffffu, slow);
+    if (SCQ_CAP < 64 && qcount + __popc(m) > (unsigned)SCQ_CAP) {               // no room: run what is waiting, part-filled
+        unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
+        sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gbase, goff, n_clamped, st, sm, lt);
+        qcount = 0;
+    }
+    if (slow) {
+        const uint32_t a = queue + (qcount + __popc(m & lt)) * 4u;
+        sts_f32(a, v.x);
+        sts_f32(a + SCQ_CAP * 4, v.y);
+        sts_f32(a + SCQ_CAP * 8, v.z);
+    }
+    qcount += __popc(m);
+    if (qcount >= 32u) {
+        qcount -= 32u;
+        unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
+        sc_exact_batch<VARIANT, FULL, SPILL>(queue, qcount, 32u, ea, gbase, goff, n_clamped, st, sm, lt);
+    }
+}
+
+// One register set -- U points per lane -- called warp-uniformly (`active` masks lanes past the end of the item).
+// Point by point: screen, commit; then ONE vote per set for the points that failed the screen.
+// (SC_BATCH = 1 screens the U points first as one branch-free block, so that ptxas interleaves the U dependent chains,
+// and commits afterwards: better ILP per warp, but the U (cell, key, valid) triples stay live, predicates get packed
+// into registers and the next set's loads issue later -- measured 6 % slower, profiles/r2_notes.md r2k.  The kernel is
+// short of bytes in flight, not of ILP: fewer, fatter threads (640 x 3, 512 x 4) are slower still.)
 // `qoff`: byte offset of the exact-path queues from the rows; the warp's own queue address and the scan's counter block
 // are only formed on the rare paths.  STATS = false: no per-scan counters are kept at all (stats == NULL).
-template <int VARIANT, bool FULL, bool DEF, bool SPILL, bool STATS>
-__device__ __forceinline__ void sc_point(const BinCfg &cfg, const ExactArgs *ea, const float4 v, const bool active,
-                                         uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped, unsigned long long *__restrict__ stats,
-                                         const int scan, const SmemRows sm, const uint32_t qoff, unsigned &qcount,
-                                         const unsigned lt, const uint32_t wtok = 0u)
+template <int VARIANT, bool FULL, bool DEF, bool SPILL, bool STATS, int U>
+__device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, const float4 (&v)[U], const bool active,
+                                       uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped, unsigned long long *__restrict__ stats,
+                                       const int scan, const SmemRows sm, const uint32_t qoff, unsigned &qcount,
+                                       const unsigned lt, const uint32_t wtok = 0u)
 {
-    int ring, sector;
-    bool beyond;
-    bool ok = dsc::screened_core_t<DEF>(cfg, v.x, v.y, 0.0f, 0.0f, &ring, &sector, &beyond);
-    if (VARIANT == 1) ok = ok && (fabsf(v.z) < INFINITY);    // finite mask (scan_context_node.py:115)
-    bool take = ok && active;
-    if (VARIANT == 1) {
-        if (STATS && take && beyond)                         // r > max_length: dropped (scan_context_node.py:134-137)
-            atomicAdd(stats + (int64_t)scan * DSC_STATS_WORDS + 4, 1ull);
-        take = take && !beyond;
-    } else if (STATS) {
-        n_clamped += (take && beyond) ? 1u : 0u;
-    }
     const int S = DEF ? dsc::defgrid::S : cfg.S;
-    sc_commit<FULL, SPILL>(FULL ? v.z : __fadd_rn(v.z, cfg.offset), ring * S + sector, take, sm, gbase, goff, lt, wtok);
-    const unsigned m = __ballot_sync(0xffffffffu, active && !ok);
-    if (m) {                                     // warp-uniform, rare
-        const uint32_t queue = sm.base + qoff + (threadIdx.x >> 5) * SCQ_WARP_BYTES;
-        if (active && !ok) {
-            const uint32_t a = queue + (qcount + __popc(m & lt)) * 4u;
-            sts_f32(a, v.x);
-            sts_f32(a + SCQ_CAP * 4, v.y);
-            sts_f32(a + SCQ_CAP * 8, v.z);
+    bool slow[U];
+#if SC_BATCH
+    int cell[U];
+    uint32_t key[U];
+    bool valid[U];
+#endif
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int ring, sector;
+        bool beyond;
+        bool ok = dsc::screened_core_t<DEF>(cfg, v[u].x, v[u].y, 0.0f, 0.0f, &ring, &sector, &beyond);
+        if (VARIANT == 1) ok = ok && (fabsf(v[u].z) < INFINITY);    // finite mask (scan_context_node.py:115)
+        bool take = ok && active;
+        if (VARIANT == 1) {
+            if (STATS && take && beyond)                         // r > max_length: dropped (scan_context_node.py:134-137)
+                atomicAdd(stats + (int64_t)scan * DSC_STATS_WORDS + 4, 1ull);
+            take = take && !beyond;
+        } else if (STATS) {
+            n_clamped += (take && beyond) ? 1u : 0u;
         }
-        qcount += __popc(m);
-        if (qcount >= 32u) {
-            qcount -= 32u;
-            unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
-            sc_exact_batch<VARIANT, FULL, SPILL>(queue, qcount, 32u, ea, gbase, goff, n_clamped, st, sm, lt);
-        }
+        const float zv = FULL ? v[u].z : __fadd_rn(v[u].z, cfg.offset);
+        slow[u] = active && !ok;
+#if SC_BATCH
+        key[u] = sc_key<FULL>(zv);
+        valid[u] = take && sc_counts<FULL>(zv);
+        cell[u] = ring * S + sector;
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) sc_commit<SPILL>(key[u], cell[u], valid[u], sm, gbase, goff, lt, u == 0 ? wtok : 0u);
+#else
+        sc_commit<SPILL>(sc_key<FULL>(zv), ring * S + sector, take && sc_counts<FULL>(zv), sm, gbase, goff, lt, u == 0 ? wtok : 0u);
+#if SC_VOTE_POINT
+        if (__any_sync(0xffffffffu, slow[u]))    // warp-uniform, rare
+            sc_park<VARIANT, FULL, SPILL, STATS>(ea, v[u], slow[u], gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
+#endif
+    }
+#endif
+#if !SC_VOTE_POINT
+    bool any_slow = slow[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u) any_slow = any_slow || slow[u];
+    if (__any_sync(0xffffffffu, any_slow)) {     // warp-uniform, rare
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            sc_park<VARIANT, FULL, SPILL, STATS>(ea, v[u], slow[u], gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
+    }
+#endif
 }
 
 // exact-only flavour (DSC_FLAG_EXACT_ONLY, non-dyadic gaps): every point takes the fdlibm chain
@@ -238,7 +348,8 @@ __device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4
     __syncwarp();
     const int status = (int)(b.x >> 27);
     n_clamped += (active && status == dsc::PT_CLAMPED) ? 1u : 0u;
-    sc_commit<FULL, SPILL>(__uint_as_float(b.y), (int)(b.x & 0x7ffffffu), active && status <= dsc::PT_CLAMPED, sm, gbase, goff, lt);
+    const float zv = __uint_as_float(b.y);
+    sc_commit<SPILL>(sc_key<FULL>(zv), (int)(b.x & 0x7ffffffu), active && status <= dsc::PT_CLAMPED && sc_counts<FULL>(zv), sm, gbase, goff, lt);
 }
 
 // end of item: the queue's remaining entries (fewer than 32)
@@ -277,24 +388,29 @@ __device__ __forceinline__ void sc_item(int item, const int64_t *__restrict__ of
     }
 }
 
+template <bool FULL>
 __device__ __forceinline__ float4 sc_decode4(const uint4 q)
 {
     float4 f;
-    f.x = dsc::key_to_float(q.x);
-    f.y = dsc::key_to_float(q.y);
-    f.z = dsc::key_to_float(q.z);
-    f.w = dsc::key_to_float(q.w);
+    if constexpr (FULL) {
+        f.x = dsc::key_to_float(q.x);
+        f.y = dsc::key_to_float(q.y);
+        f.z = dsc::key_to_float(q.z);
+        f.w = dsc::key_to_float(q.w);
+    } else {                                     // offset mode: the keys are the floats (sc_key)
+        f = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+    }
     return f;
 }
 
 // decode `nvec` 128-bit groups of keys from shared memory to floats, re-zeroing the rows
-template <int NT>
+template <int NT, bool FULL>
 __device__ __forceinline__ void sc_flush_rows(uint32_t *__restrict__ srows, float4 *__restrict__ dst, int nvec)
 {
     for (int i = threadIdx.x; i < nvec; i += NT) {
         const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
         reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
-        __stcs(dst + i, sc_decode4(q));
+        __stcs(dst + i, sc_decode4<FULL>(q));
     }
 }
 
@@ -315,7 +431,7 @@ __device__ __forceinline__ void sc_band_entry(const uint32_t cell, const uint32_
 
 // End of a whole-scan item (this CTA owns the scan): write out the resident rows, then reduce and write out the other
 // rings band by band from the spill lists.  `wseg`: this warp's list of `len` entries.  Ends with a CTA barrier.
-template <int NT>
+template <int NT, bool FULL>
 __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, const uint32_t sbase,
                                                float *__restrict__ out_scan, const int ns, const int r0, const int R,
                                                const int S, const uint2 *__restrict__ wseg, const int len)
@@ -325,8 +441,8 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
     const int lane2 = 2 * (int)(threadIdx.x & 31u);
     __syncthreads();                             // every shared-memory atomic and every list store of the item is done
     // resident rows: rings r0 .. r0+ns-2, and the clamp ring R-1 kept in row ns-1
-    sc_flush_rows<NT>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
-    sc_flush_rows<NT>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
+    sc_flush_rows<NT, FULL>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
+    sc_flush_rows<NT, FULL>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
     // remaining rings, numbered v = 0 .. R-ns-1: ring v below the window, ring v + ns - 1 above it
     const int nv = R - ns;
     for (int b0 = 0; b0 < nv; b0 += ns) {
@@ -355,15 +471,15 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
         }
 #endif
         __syncthreads();
-        sc_flush_rows<NT>(srows, oq + (size_t)b0 * rowvec, rows1 * rowvec);
-        sc_flush_rows<NT>(srows + (size_t)rows1 * S, oq + (size_t)ring2 * rowvec, rows2 * rowvec);
+        sc_flush_rows<NT, FULL>(srows, oq + (size_t)b0 * rowvec, rows1 * rowvec);
+        sc_flush_rows<NT, FULL>(srows + (size_t)rows1 * S, oq + (size_t)ring2 * rowvec, rows2 * rowvec);
     }
     __syncthreads();                             // rows are zero before the next scan's atomics
 }
 
 // End of a whole-scan item, SC_SLOT form: the non-resident rings were reduced with RED.MAX on the CTA's private L2 slot
 // (a full key grid, zero == empty); decode resident rows and slot to floats and re-zero both.  Ends with a CTA barrier.
-template <int NT, int DU = 4>
+template <int NT, bool FULL, int DU = 4>
 __device__ __forceinline__ void sc_finish_slot(uint32_t *__restrict__ srows, uint32_t *__restrict__ slot,
                                                float *__restrict__ out_scan, const int ns, const int r0, const int R, const int S)
 {
@@ -371,8 +487,8 @@ __device__ __forceinline__ void sc_finish_slot(uint32_t *__restrict__ srows, uin
     float4 *oq = reinterpret_cast<float4 *>(out_scan);
     __threadfence();                             // our REDs are performed ...
     __syncthreads();                             // ... before any thread of the CTA reads the keys back
-    sc_flush_rows<NT>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
-    sc_flush_rows<NT>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
+    sc_flush_rows<NT, FULL>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
+    sc_flush_rows<NT, FULL>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
     uint4 *kq = reinterpret_cast<uint4 *>(slot);
     // rings 0 .. r0-1 and r0+ns-1 .. R-2, as one index range with a jump over the window
     const int n_lo = r0 * rowvec, n_tot = (R - ns) * rowvec, jump = (ns - 1) * rowvec;
@@ -388,7 +504,7 @@ __device__ __forceinline__ void sc_finish_slot(uint32_t *__restrict__ srows, uin
             const int j = j0 + d * NT;
             if (j < n_tot) {
                 const int i = j < n_lo ? j : j + jump;
-                __stcs(oq + i, sc_decode4(q[d]));
+                __stcs(oq + i, sc_decode4<FULL>(q[d]));
                 if (q[d].x | q[d].y | q[d].z | q[d].w) __stcg(kq + i, make_uint4(0, 0, 0, 0));
             }
         }
@@ -399,7 +515,7 @@ __device__ __forceinline__ void sc_finish_slot(uint32_t *__restrict__ srows, uin
 
 // End of a split work item: fold the resident rows into the scan's key grid (== its output grid), count the item as
 // retired, and if it was the scan's last item decode the grid in place.  Ends with a CTA barrier.
-template <int NT, int DU = 4>
+template <int NT, bool FULL, int DU = 4>
 __device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, uint32_t *__restrict__ grid, int ns, int r0,
                                                 int R, int S, int scan, int parts, unsigned int *__restrict__ done,
                                                 int *s_last)
@@ -428,7 +544,7 @@ __device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, ui
         if (prev + 1u == (unsigned)parts) __threadfence();         // acquire: the other CTAs' REDs are visible
     }
     __syncthreads();
-    if (*s_last) {
+    if (FULL && *s_last) {                       // (offset mode: the keys are the floats already)
         uint4 *kq = reinterpret_cast<uint4 *>(grid);
         const int nvec = cells >> 2;
         for (int i0 = tid; i0 < nvec; i0 += NT * DU) {
@@ -441,7 +557,7 @@ __device__ __forceinline__ void sc_finish_split(uint32_t *__restrict__ srows, ui
 #pragma unroll
             for (int d = 0; d < DU; ++d) {
                 const int i = i0 + d * NT;
-                if (i < nvec) __stcs(reinterpret_cast<float4 *>(kq) + i, sc_decode4(q[d]));
+                if (i < nvec) __stcs(reinterpret_cast<float4 *>(kq) + i, sc_decode4<true>(q[d]));
             }
         }
     }
@@ -484,7 +600,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     // SR_LTMASK or rebuilding the shared-window address costs 1-5 instructions per point in an issue-bound loop)
     sm.base = __shfl_sync(0xffffffffu, sm.base, 0);
     const unsigned lt = __shfl_sync(0xffffffffu, lanemask_lt(), (int)(tid & 31));
-    sm.c0 = r0 * S;
+    sm.c0 = __shfl_sync(0xffffffffu, r0 * S, 0);     // (same: otherwise re-derived from r0 with two instructions per point)
     sm.lim = (ns - 1) * S;                       // host guarantees ns >= 2
     sm.last = (R - 1) * S;
     sm.shift = sm.lim - sm.last;
@@ -516,29 +632,90 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             } else if constexpr (SC_SLOT) {
                 gbase = reinterpret_cast<uint32_t *>(spill) + (size_t)blockIdx.x * (size_t)cells;
             } else {
+                // the write position counts entries from the start of the launch's spill buffer (host guarantees
+                // gridDim.x * spill_cap < 2^32): the store address is one multiply-add away from it
                 const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;       // most points one warp can see
-                gbase = reinterpret_cast<uint32_t *>(spill + (size_t)blockIdx.x * spill_cap);
-                goff = (uint32_t)(tid >> 5) * seg;
+                gbase = reinterpret_cast<uint32_t *>(spill);
+                goff = blockIdx.x * (uint32_t)spill_cap + (uint32_t)(tid >> 5) * seg;
             }
             // the stream position is a 32-bit index of 16-byte rows from `pts` (host guarantees < 2^32 rows per call):
             // one register across the loop instead of a 64-bit pointer
             const float4 *const pts4 = reinterpret_cast<const float4 *>(pts);
             unsigned n_clamped = 0;
+#if SC_ASYNC
+            // The stream goes global -> shared with 16-byte asynchronous copies (LDGSTS.BYPASS: past L1, past the register
+            // file), one point per thread per group, into a ring of SC_NG groups behind the exact-path queues; each thread
+            // reads back only what it copied itself, so cp.async.wait_group is all the synchronisation there is.  SC_NG-1
+            // groups (NT * 16 B each) are in flight at any time, whatever the register budget.
+            {
+                constexpr int NG = SC_NG;
+                constexpr uint32_t GB = (uint32_t)NT * 16u;
+                const uint32_t stg = sm.base + qoff + (FAST ? (uint32_t)(NT / 32) * SCQ_WARP_BYTES : 0u) + (uint32_t)tid * 16u;
+                const int ngroups = (n + NT - 1) / NT;
+                const int nfullg = n / NT;                                     // groups in which every thread has a point
+                int rem = n - tid;                                               // > k * NT  <=>  this thread has a point in group k
+                uint32_t pf = (uint32_t)p0 + (uint32_t)tid;                      // row of this thread's point in the next group to fetch
+#define SC_FETCH(slot, pred)                                                                                    \
+    do {                                                                                                        \
+        if (pred) cp_async16(stg + (uint32_t)(slot) * GB, pts4 + pf, pol_stream);                               \
+        cp_async_commit();                                                                                      \
+        pf += NT;                                                                                               \
+    } while (0)
+#define SC_ONE(vv, act)                                                                                         \
+    do {                                                                                                        \
+        if constexpr (FAST) sc_set<VARIANT, FULL, DEF, SPILL, STATS, 1>(cfg, &s_ea, (vv), (act), gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt); \
+        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (vv)[0], (act), gbase, goff, n_clamped, stats, scan, sm, lt); \
+    } while (0)
+#pragma unroll
+                for (int g = 0; g < NG - 1; ++g) SC_FETCH(g, rem > g * NT);
+                int k0 = 0;
+                for (; k0 + 2 * NG - 1 <= nfullg; k0 += NG) {                    // every group touched here is full: no predicates
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        SC_FETCH((g + NG - 1) % NG, true);
+                        cp_async_wait<NG - 1>();
+                        float4 v[1] = {lds_f4(stg + (uint32_t)g * GB)};
+                        SC_ONE(v, true);
+                    }
+                }
+                rem -= k0 * NT;
+                for (; k0 < ngroups; k0 += NG) {                                 // the last groups
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        if (k0 + g < ngroups) {                                  // CTA-uniform
+                            SC_FETCH((g + NG - 1) % NG, rem > (NG - 1) * NT);
+                            cp_async_wait<NG - 1>();
+                            float4 v[1] = {lds_f4(stg + (uint32_t)g * GB)};
+                            const bool act = rem > 0;
+                            rem -= NT;
+                            SC_ONE(v, act);
+                        }
+                    }
+                }
+                cp_async_wait<0>();
+#undef SC_FETCH
+#undef SC_ONE
+            }
+#else
             const int nfull = n / STEP;
             uint32_t p = (uint32_t)p0 + (uint32_t)tid;
             float4 a[U], b[U];
 #define SC_LD(idx) ld_stream_f4_hint(pts4 + (idx), pol_stream)
-#define SC_PT(v, act, tok)                                                                                         \
+#define SC_SET(v, tok)                                                                                          \
     do {                                                                                                        \
-        if constexpr (FAST) sc_point<VARIANT, FULL, DEF, SPILL, STATS>(cfg, &s_ea, (v), (act), gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt, (tok)); \
-        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v), (act), gbase, goff, n_clamped, stats, scan, sm, lt);      \
+        if constexpr (FAST) {                                                                                   \
+            sc_set<VARIANT, FULL, DEF, SPILL, STATS, U>(cfg, &s_ea, (v), true, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt, (tok)); \
+        } else {                                                                                                \
+            _Pragma("unroll") for (int u = 0; u < U; ++u)                                                       \
+                sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v)[u], true, gbase, goff, n_clamped, stats, scan, sm, lt); \
+        }                                                                                                       \
     } while (0)
             // SC_TOK: one real use of the (dead) intensity words of a register set when its processing starts.  Without it
             // ptxas hands those registers -- the fourth destination registers of 128-bit loads that are still in
             // flight -- to instructions of the set processed BEFORE, which then wait for the whole load (write-after-
             // write on the long scoreboard: one POPC held 20 % of all stall samples in profiles/r2d_*) and the register
             // ping-pong is defeated.  The XOR of the words becomes the scratch destination of the first point's LDS.
-#define SC_TOK(s) (U == 3 ? sc_tok3((s)[0].w, (s)[1].w, (s)[2].w) : sc_tok2((s)[0].w, (s)[U - 1].w))
+#define SC_TOK(s) (U == 4 ? sc_tok3((s)[0].w, (s)[1].w, (s)[2].w) ^ __float_as_uint((s)[U - 1].w) : U == 3 ? sc_tok3((s)[0].w, (s)[1].w, (s)[2].w) : sc_tok2((s)[0].w, (s)[U - 1].w))
             if (nfull > 0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
@@ -548,8 +725,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 #pragma unroll
                 for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * NT);
                 const uint32_t ta = SC_TOK(a);
-#pragma unroll
-                for (int u = 0; u < U; ++u) SC_PT(a[u], true, u == 0 ? ta : 0u);
+                SC_SET(a, ta);
                 p += 2 * STEP;
                 step += 2;
                 if (step < nfull) {
@@ -557,25 +733,25 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
                     for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
                 }
                 const uint32_t tb = SC_TOK(b);
-#pragma unroll
-                for (int u = 0; u < U; ++u) SC_PT(b[u], true, u == 0 ? tb : 0u);
+                SC_SET(b, tb);
             }
             if (step < nfull) {
                 const uint32_t ta = SC_TOK(a);
-#pragma unroll
-                for (int u = 0; u < U; ++u) SC_PT(a[u], true, u == 0 ? ta : 0u);
+                SC_SET(a, ta);
             }
 #undef SC_TOK
+#undef SC_SET
             for (int i0 = nfull * STEP; i0 < n; i0 += NT) {       // ragged tail, warp-uniform trip count
                 const bool act = i0 + tid < n;
-                float4 v = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
-                if (act) v = SC_LD((uint32_t)p0 + (uint32_t)(i0 + tid));
-                SC_PT(v, act, 0u);
+                float4 v[1] = {make_float4(1.0f, 1.0f, 0.0f, 0.0f)};
+                if (act) v[0] = SC_LD((uint32_t)p0 + (uint32_t)(i0 + tid));
+                if constexpr (FAST) sc_set<VARIANT, FULL, DEF, SPILL, STATS, 1>(cfg, &s_ea, v, act, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
+                else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, v[0], act, gbase, goff, n_clamped, stats, scan, sm, lt);
             }
+#undef SC_LD
+#endif
             unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
             if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gbase, goff, n_clamped, st, sm, qoff, qcount, lt);
-#undef SC_LD
-#undef SC_PT
             if (STATS) {
                 const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
                 if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
@@ -589,14 +765,13 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             int64_t p0;
             sc_item<SPLIT>(item2, offsets, n_scans, sp, scan, parts, p0, n);
             if constexpr (SPLIT) {
-                sc_finish_split<NT, SC_DU>(srows, gbase, ns, r0, R, S, scan, parts, sp.done, &s_last);
+                sc_finish_split<NT, FULL, SC_DU>(srows, gbase, ns, r0, R, S, scan, parts, sp.done, &s_last);
             } else if constexpr (SC_SLOT) {
-                sc_finish_slot<NT, SC_DU>(srows, gbase, out + (size_t)scan * cells, ns, r0, R, S);
+                sc_finish_slot<NT, FULL, SC_DU>(srows, gbase, out + (size_t)scan * cells, ns, r0, R, S);
             } else {
                 const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;
-                const uint32_t w0 = (uint32_t)(tid >> 5) * seg;
-                sc_finish_scan<NT>(srows, sm.base, out + (size_t)scan * cells, ns, r0, R, S,
-                                   spill + (size_t)blockIdx.x * spill_cap + w0, (int)(goff - w0));
+                const uint32_t w0 = blockIdx.x * (uint32_t)spill_cap + (uint32_t)(tid >> 5) * seg;
+                sc_finish_scan<NT, FULL>(srows, sm.base, out + (size_t)scan * cells, ns, r0, R, S, spill + w0, (int)(goff - w0));
             }
         }
         par ^= 1;

@@ -178,7 +178,8 @@ struct BinCfg {
     int32_t fast_ok;
     float   fast_dr, fast_ds;        // half-widths of the "too close to a boundary" bands (bin units)
     float   q90, q180, q360;         // 90/180/360 degrees in sector units (exact: pow2 scaling)
-    float   Rp1_f;                   // (float)(R + 1)
+    float   R_f;                     // (float)R
+    float   fast_hr, fast_hs;        // 0.5 - fast_dr, 0.5 - fast_ds
     float   atan_c[8];               // atan(u)/u minimax in u^2 on [0,1], pre-scaled to sector units
 };
 
@@ -220,9 +221,11 @@ static inline BinCfg make_bin_cfg(int R, int S, double max_length, int variant, 
         c.q90 = (float)(90.0 * inv_s);
         c.q180 = (float)(180.0 * inv_s);
         c.q360 = (float)(360.0 * inv_s);
-        c.Rp1_f = (float)(R + 1);
+        c.R_f = (float)R;
         c.fast_dr = (float)((R + 1) * 1.5e-6);
         c.fast_ds = (float)(5.0e-4 * inv_s);
+        c.fast_hr = 0.5f - c.fast_dr;
+        c.fast_hs = 0.5f - c.fast_ds;
     }
     return c;
 }
@@ -320,27 +323,32 @@ DSC_HD BinResult bin_exact(const BinCfg &c, float x, float y, float z)
 // ---- screened fast path --------------------------------------------------------------------------
 // The exact chain above costs ~100 instructions per point (two IEEE divisions, an IEEE sqrt and 26
 // unfused polynomial steps).  Almost every point sits far from any bin boundary, where a much
-// cheaper approximation provably lands in the same bin.  bin_screened() computes
+// cheaper approximation provably lands in the same bin.  screened_core_t() computes
 //     qr ~ r / gap_ring        (fma + MUFU.SQRT)                          in ring units
 //     qs ~ theta / gap_sector  (MUFU.RCP + 8-term minimax atan, octant fix-up)  in sector units
 // and accepts the floor() of each only when the value is at least fast_dr / fast_ds away from every
 // integer.  Anything else -- including every NaN/Inf/overflow/underflow, which turn into NaN or land
-// on a boundary -- reports *slow and is re-done by bin_exact().
+// on a boundary -- reports "not ok" and is re-done by bin_exact().
+//
+// floor() and the distance to the bin centre come from one magic-number addition rounded toward minus infinity:
+// t = q + 2^23 (add.rm) is 2^23 + floor(q), its low mantissa bits ARE the bin index, and q - (t - (2^23 - 1/2)) is the
+// offset from the bin centre, which must stay below 1/2 - band.  Three FADDs and an integer subtract on the FMA/ALU
+// pipes; the cvt.rni / cvt.rzi pair they replace (FRND, F2I) runs on the quarter-rate XU pipe next to MUFU.SQRT and
+// MUFU.RCP, which was the busiest pipe of k1_scan (42 %, profiles/r2e_k1_scan.*).
 //
 // Error budget (degrees; true = real-number polar coordinates of the float inputs):
 //   reference chain vs true : atan2f < 1 ulp(pi) = 1.4e-5, y/x rounding 1.7e-6, rad2deg multiply
 //                             7.6e-6 + constant 6e-6, (+360) rounding 1.5e-5      => < 5e-5
 //   fast chain vs true      : polynomial 7.4e-6 (measured in f32), rcp.approx+mul 6.9e-6, three
 //                             octant subtractions <= 3e-5                          => < 4.5e-5
-//   sum 9.5e-5 deg; band fast_ds = 5e-4 deg (5x).
+//   sum 9.5e-5 deg; band fast_ds = 5e-4 deg (5x).  (The centre offset q - (floor + 1/2) is exact.)
 //   ring: sqrt.approx 2^-23 + one multiply + the fma-vs-unfused difference < 3e-7 relative,
 //   i.e. < (R+1)*3e-7 ring units; band fast_dr = (R+1)*1.5e-6 (5x).
 #if defined(__CUDA_ARCH__)
 DSC_HD float approx_sqrt(float s, float) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s)); return r; }
 DSC_HD float approx_rcp(float s, float) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s)); return r; }
 DSC_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-DSC_HD float round_nearest(float a) { return rintf(a); }
-DSC_HD int f2i_sat(float a, float hi) { (void)hi; return __float2int_rz(a); }    // cvt.rzi saturates; NaN -> 0
+DSC_HD float fadd_floor_magic(float a) { return __fadd_rd(a, 8388608.0f); }
 #else
 // host emulation for tests/host_math.cpp: correctly rounded value perturbed by `noise` * 2^-22
 // (|noise| <= 1 covers the documented MUFU error), with flush-to-zero of subnormal operands/results
@@ -359,9 +367,11 @@ DSC_HD float approx_rcp(float s, float noise)
     return r;
 }
 DSC_HD float ffma(float a, float b, float c) { return (float)((double)a * (double)b + (double)c); }
-DSC_HD float round_nearest(float a) { return nearbyintf(a); }
-DSC_HD int f2i_sat(float a, float hi) { return (int)fminf(a, hi); }              // same values wherever the screen says ok
+DSC_HD float fadd_floor_magic(float a) { return (float)(floor((double)a) + 8388608.0); }   // add.rm for 0 <= a < 2^23 (NaN stays NaN)
 #endif
+
+#define DSC_FLOOR_MAGIC_U 0x4b000000u     // bits of 2^23
+#define DSC_FLOOR_MAGIC_H 8388607.5f      // 2^23 - 1/2
 
 // Core of the screen: true when (ring, sector, beyond) are certain; false sends the point to bin_exact.
 // No zero substitution is needed here: a zero coordinate makes u == 0 (or NaN), so the approximate
@@ -377,8 +387,9 @@ constexpr float c0 = (float)(0.9999993443489075 * kScale), c1 = (float)(-0.33329
                 c4 = (float)(0.09642194956541061 * kScale), c5 = (float)(-0.05591229721903801 * kScale),
                 c6 = (float)(0.0218629352748394 * kScale), c7 = (float)(-0.004054560791701078 * kScale);
 constexpr int R = 160, S = 720;
-constexpr float q90 = 180.0f, q180 = 360.0f, q360 = 720.0f, Rp1_f = 161.0f;
+constexpr float q90 = 180.0f, q180 = 360.0f, q360 = 720.0f, R_f = 160.0f;
 constexpr float fast_dr = (float)(161 * 1.5e-6), fast_ds = (float)(5.0e-4 * 2.0);
+constexpr float fast_hr = 0.5f - fast_dr, fast_hs = 0.5f - fast_ds;
 }  // namespace defgrid
 
 template <bool DEF>
@@ -386,10 +397,11 @@ DSC_HD bool screened_core_t(const BinCfg &c, float x, float y, float noise_r, fl
                             int *sector, bool *beyond)
 {
     const float ax = fabsf(x), ay = fabsf(y);
-    // ring coordinate: sqrt.approx.ftz flushes a subnormal s to 0 (-> boundary 0 -> exact path);
-    // an overflowing s gives +inf, rejected by the explicit finite test
+    // ring coordinate: sqrt.approx.ftz flushes a subnormal s to 0 (-> boundary 0 -> exact path); an overflowing s is
+    // rejected by the explicit test below.  From the middle of ring R on ("beyond": clamped by variant A, dropped by
+    // variant B) the value is pinned to R + 1/2, a bin centre, which takes the far zone out of the boundary test.
     const float s = ffma(x, x, y * y);
-    const float qr = approx_sqrt(s, noise_r) * c.inv_gap_ring_f;
+    const float qr = fminf(approx_sqrt(s, noise_r) * c.inv_gap_ring_f, (DEF ? defgrid::R_f : c.R_f) + 0.5f);
     // sector coordinate
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float u = mn * approx_rcp(mx, noise_t);
@@ -405,17 +417,16 @@ DSC_HD bool screened_core_t(const BinCfg &c, float x, float y, float noise_r, fl
     if (ay > ax) qs = (DEF ? defgrid::q90 : c.q90) - qs;
     if (x < 0.0f) qs = (DEF ? defgrid::q180 : c.q180) - qs;
     if (y < 0.0f) qs = (DEF ? defgrid::q360 : c.q360) - qs;
-    // distance to the nearest bin boundary (NaN compares false everywhere => not ok)
-    const float dr = fabsf(qr - round_nearest(qr)), ds = fabsf(qs - round_nearest(qs));
-    const float Rp1 = DEF ? defgrid::Rp1_f : c.Rp1_f;
+    // bin index and offset from the bin centre (NaN compares false everywhere => not ok); qr, qs >= 0 or NaN
+    const float tr = fadd_floor_magic(qr), ts = fadd_floor_magic(qs);
+    const float er = fabsf(qr - (tr - DSC_FLOOR_MAGIC_H)), es = fabsf(qs - (ts - DSC_FLOOR_MAGIC_H));
+    const bool ok = (es < (DEF ? defgrid::fast_hs : c.fast_hs)) && (er < (DEF ? defgrid::fast_hr : c.fast_hr)) &&
+                    (s < INFINITY);
     const int Rr = DEF ? defgrid::R : c.R;
-    const bool far_out = qr >= Rp1;                      // deep in the clamp / reject zone
-    const bool ok = (ds > (DEF ? defgrid::fast_ds : c.fast_ds)) &&
-                    (far_out || dr > (DEF ? defgrid::fast_dr : c.fast_dr)) && (qr < INFINITY);
-    const int ir = f2i_sat(qr, Rp1);                     // qr >= 0: truncation == floor; saturating, so the cast is defined
+    const int ir = (int)(f2u(tr) - DSC_FLOOR_MAGIC_U);   // 0 .. R wherever ok
     *beyond = ir >= Rr;
     *ring = min_i(ir, Rr - 1);
-    *sector = (int)qs;
+    *sector = (int)(f2u(ts) - DSC_FLOOR_MAGIC_U);        // 0 .. S-1 wherever ok
     return ok;
 }
 
@@ -423,7 +434,8 @@ static inline bool is_default_grid(const BinCfg &c)
 {
     return c.fast_ok && c.R == defgrid::R && c.S == defgrid::S && c.atan_c[0] == defgrid::c0 &&
            c.atan_c[7] == defgrid::c7 && c.q90 == defgrid::q90 && c.q360 == defgrid::q360 &&
-           c.Rp1_f == defgrid::Rp1_f && c.fast_dr == defgrid::fast_dr && c.fast_ds == defgrid::fast_ds;
+           c.R_f == defgrid::R_f && c.fast_dr == defgrid::fast_dr && c.fast_ds == defgrid::fast_ds &&
+           c.fast_hr == defgrid::fast_hr && c.fast_hs == defgrid::fast_hs;
 }
 
 DSC_HD bool screened_core(const BinCfg &c, float x, float y, float noise_r, float noise_t, int *ring,
