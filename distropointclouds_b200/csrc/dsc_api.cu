@@ -82,7 +82,7 @@ extern "C" int dsc_set_option(dsc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "sc_split") && value >= -1 && value <= 1) { ctx->sc_split = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_item_points") && value >= 1024 && value <= (1 << 30)) { ctx->sc_item_points = (int)value; return DSC_OK; }
     if (!strcmp(name, "sc_window") && value >= -1 && value <= 65536) { ctx->sc_window = (int)value; return DSC_OK; }
-    if (!strcmp(name, "sc_cfg") && value >= 0 && value <= 7) { ctx->sc_cfg = (int)value; return DSC_OK; }
+    if (!strcmp(name, "sc_cfg") && value >= -1 && value <= 7) { ctx->sc_cfg = (int)value; return DSC_OK; }
     DSC_FAIL(ctx, DSC_ERR_INVALID, std::string("unknown option or bad value: ") + name);
 }
 extern "C" float dsc_last_kernel_ms(const dsc_ctx *ctx) { return ctx ? ctx->last_ms : -1.0f; }

@@ -149,15 +149,18 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
                              split_items > n_scans);
     const bool split = sc_shape_ok && want_split && split_items < 0x7fff0000LL;
     const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
-    // launch shape (threads x 128-bit loads per thread per register set); shapes other than 0 exist for the
-    // screened default-grid kernels only.  Fewer threads = more registers per thread (no spills), fewer warps.
-    int shape = (cfg.fast_ok && defgrid) ? ctx->sc_cfg : 2;                     // the generic kernels are 1024 x 2
-#ifdef SC_EXTRA_SHAPES                            // A/B builds: 640 x 3 (102 registers), 512 x 4 (128), 512 x 3
+    // launch shape (threads x 128-bit loads per thread per register set); shapes other than 2 exist for the screened
+    // default-grid kernels only.  More threads = more warps to hide the load latency with and more bytes in flight per
+    // register set, but fewer registers per thread: 896 x 3 (72 registers, nothing spilled on the streaming path) beats
+    // 768 x 3 (80) by 1.5 %, 1024 x 3 / 1024 x 2 (64, spills in the loop) lose 8-10 % (profiles/r2_notes.md, r2n).
+    // Split items reduce with RED.MAX on a grid shared by several CTAs and prefer 768 x 3 (dense2m: 0.58 ms vs 0.71 ms).
+    int shape = (cfg.fast_ok && defgrid) ? (ctx->sc_cfg >= 0 ? ctx->sc_cfg : (split ? 1 : 0)) : 2;   // the generic kernels are 1024 x 2
+#ifdef SC_EXTRA_SHAPES                            // A/B builds: 640 x 3, 512 x 4, 512 x 3, 1024 x 3, 832 x 3
     if (shape < 0 || shape > 7) shape = 0;
-    const int nthreads = shape == 0 ? 768 : shape == 3 ? 640 : shape == 6 ? 896 : shape == 7 ? 832 : shape >= 4 ? 512 : 1024;
+    const int nthreads = shape == 0 ? 896 : shape == 1 ? 768 : shape == 3 ? 640 : shape == 7 ? 832 : (shape == 4 || shape == 5) ? 512 : 1024;
 #else
     if (shape != 1 && shape != 2) shape = 0;
-    const int nthreads = shape == 0 ? 768 : 1024;
+    const int nthreads = shape == 0 ? 896 : shape == 1 ? 768 : 1024;
 #endif
     const size_t row_bytes = (size_t)p->num_sector * 4;
     const size_t q_bytes = cfg.fast_ok ? (size_t)SCQ_WARP_BYTES * (nthreads / 32) : 0;       // per-warp exact-path queues
@@ -278,17 +281,17 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         else if (shape == 3) SC_LAUNCH3(true, V, H, 3, 640, true);                                              \
         else if (shape == 4) SC_LAUNCH3(true, V, H, 4, 512, true);                                              \
         else if (shape == 5) SC_LAUNCH3(true, V, H, 3, 512, true);                                              \
-        else if (shape == 6) SC_LAUNCH3(true, V, H, 3, 896, true);                                              \
+        else if (shape == 6) SC_LAUNCH3(true, V, H, 3, 1024, true);                                             \
         else if (shape == 7) SC_LAUNCH3(true, V, H, 3, 832, true);
 #else
 #define SC_EXTRA_LAUNCH(V, H)
 #endif
 #define SC_LAUNCH_DEF(V, H)                                                                                     \
     do {                                                                                                        \
-        if (shape == 1) SC_LAUNCH3(true, V, H, 3, 1024, true);                                                  \
+        if (shape == 1) SC_LAUNCH3(true, V, H, 3, 768, true);                                                   \
         else if (shape == 2) SC_LAUNCH3(true, V, H, 2, 1024, true);                                             \
         SC_EXTRA_LAUNCH(V, H)                                                                                   \
-        else SC_LAUNCH3(true, V, H, 3, 768, true);                                                              \
+        else SC_LAUNCH3(true, V, H, 3, 896, true);                                                              \
     } while (0)
         if (cfg.fast_ok && defgrid) {
             if (p->variant == 0) { if (full) SC_LAUNCH_DEF(0, true); else SC_LAUNCH_DEF(0, false); }

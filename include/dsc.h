@@ -95,10 +95,11 @@ const char *dsc_last_error(const dsc_ctx *ctx);
  * (dsc_set_timing(ctx,1)); the call then synchronises the stream.  -1 if not available. */
 int dsc_set_timing(dsc_ctx *ctx, int enabled);
 float dsc_last_kernel_ms(const dsc_ctx *ctx);
-/* Engine options (debugging / A-B measurements; defaults are the measured best, see profiles/r1_notes.md):
+/* Engine options (debugging / A-B measurements; defaults are the measured best, see profiles/r1_notes.md and profiles/r2_notes.md):
  *   "k1_impl"        0 = auto (k1_scan; generic kernels for 12-byte stride / odd shapes / few small scans),
  *                    1 = generic L2-key kernels only, 3 = k1_scan whenever the shape allows
- *   "sc_cfg"         k1_scan launch shape: 0 = 768 threads x 3 loads, 1 = 1024 x 3, 2 = 1024 x 2
+ *   "sc_cfg"         k1_scan launch shape: -1 = auto (896 threads x 3 loads per register set for whole scans, 768 x 3 when
+ *                    scans are cut into work items), 0 = 896 x 3, 1 = 768 x 3, 2 = 1024 x 2
  *   "sc_smem_rows"   resident ring rows of k1_scan (-1 = as many as the carve-out allows)
  *   "sc_window"      first ring of k1_scan's resident window (-1 = chosen per call by k1_probe from a ring histogram
  *                    of sampled points; the grids never depend on it)
