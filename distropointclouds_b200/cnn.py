@@ -11,6 +11,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
+from . import _ffi
 from .engine import Engine, ScanContextParams, default_engine, pack_scans
 
 # (kind, in, out) per layer of tiny_sc_ped.TinyCNN; 'P' = MaxPool2d(2).  Index positions inside the two
@@ -115,13 +116,24 @@ class ScanContextCnnPipeline:
 
     # -- stages ------------------------------------------------------------------------------------
     def build_grids(self, pts, offsets: np.ndarray, params: ScanContextParams, want_norm: bool = True,
-                    stride_bytes: int = 16):
-        """K1 (+K4) on a device-resident packed point tensor.  Returns (grids, norm|None) CUDA tensors."""
+                    stride_bytes: int = 16, strict: bool = False):
+        """K1 (+K4) on a device-resident packed point tensor.  Returns (grids, norm|None) CUDA tensors.
+        strict: per-scan counters are kept and read back (one small D2H), and an IndexError is raised where the
+        reference's variant A would raise one -- NaN / Inf coordinates or an angle that rounds to 360.0
+        (scaner_version2.py:93-107); without it such points are dropped silently."""
         torch = self.torch
         n = len(offsets) - 1
         grids = torch.empty((n, params.num_ring, params.num_sector), dtype=torch.float32, device=self.device)
         norm = torch.empty_like(grids) if want_norm else None
-        self.engine.build_device(pts, offsets, params, grids, norm, None, stride_bytes)
+        stats = torch.zeros((n, len(_ffi.STATS_FIELDS)), dtype=torch.int64, device=self.device) if strict else None
+        self.engine.build_device(pts, offsets, params, grids, norm, stats, stride_bytes)
+        if strict and params.variant == _ffi.VARIANT_A:
+            st = stats.cpu().numpy()
+            bad = np.flatnonzero((st[:, 1] + st[:, 2]) > 0)
+            if bad.size:
+                k = int(bad[0])
+                raise IndexError(f"scan {k}: {int(st[k, 1])} point(s) with non-finite polar coordinates, "
+                                 f"{int(st[k, 2])} whose angle rounds to 360.0 (the reference raises IndexError here)")
         return grids, norm
 
     def logits_from_norm(self, norm):
@@ -144,21 +156,21 @@ class ScanContextCnnPipeline:
 
     # -- whole pipeline ----------------------------------------------------------------------------
     def infer_device(self, pts, offsets: np.ndarray, params: ScanContextParams = ScanContextParams(),
-                     thr: float = 0.5, stride_bytes: int = 16):
-        """Returns (grids, logits, mask uint8) as CUDA tensors; nothing touches the host."""
-        grids, norm = self.build_grids(pts, offsets, params, True, stride_bytes)
+                     thr: float = 0.5, stride_bytes: int = 16, strict: bool = False):
+        """Returns (grids, logits, mask uint8) as CUDA tensors; nothing touches the host (unless strict)."""
+        grids, norm = self.build_grids(pts, offsets, params, True, stride_bytes, strict)
         logits = self.logits_from_norm(norm)
         mask = (self.torch.sigmoid(logits) > thr).to(self.torch.uint8)                 # tiny_sc_ped.py:227-228
         return grids, logits, mask
 
     def infer_scans(self, scans: Sequence[np.ndarray], params: ScanContextParams = ScanContextParams(),
-                    thr: float = 0.5):
+                    thr: float = 0.5, strict: bool = True):
         """Host scans (list of (N,3|4) float32) -> (grids, probs, masks) NumPy arrays, like run_inference
-        (tiny_sc_ped.py:217-234) for a batch."""
+        (tiny_sc_ped.py:217-234) for a batch; strict: raise where the reference's grid builder would."""
         torch = self.torch
         pts, offsets, stride = pack_scans(list(scans))
         d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to(self.device)
-        grids, logits, mask = self.infer_device(d_pts, offsets, params, thr, stride)
+        grids, logits, mask = self.infer_device(d_pts, offsets, params, thr, stride, strict)
         return grids.cpu().numpy(), torch.sigmoid(logits).cpu().numpy(), mask.cpu().numpy()
 
 

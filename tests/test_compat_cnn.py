@@ -203,6 +203,14 @@ def test_cnn_pipeline_logits_match_reference(golden_scans, golden_grids):
         fast = ScanContextCnnPipeline(w, 0, prec)
         _, lg, _ = fast.infer_device(pts, offs, ScanContextParams())
         np.testing.assert_allclose(lg[0].cpu().numpy(), ref, rtol=0, atol=tol)
+    # a scan on which the reference's grid builder raises (NaN coordinate -> INT_MIN index, scaner_version2.py:93-107):
+    # the host entry point raises too; strict=False drops the point and keeps going
+    bad = scans[0][:1000, :3].copy()
+    bad[17, 0] = np.nan
+    with pytest.raises(IndexError):
+        pipe.infer_scans([scans[1][:, :3], bad])
+    g3, _, _ = pipe.infer_scans([scans[1][:, :3], bad], strict=False)
+    assert np.array_equal(g3[0], golden_grids["002073"])
 
 
 @pytest.mark.gpu
