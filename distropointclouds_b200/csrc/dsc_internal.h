@@ -26,7 +26,7 @@ struct dsc_ctx {
     int timing = 0;
     int sc_smem_rows = -1;           // scan kernel: ring rows kept in shared memory (-1 = as many as fit, 0 = none)
     int no_defgrid = 0;              // 1: do not use the default-grid specialisation (A/B runs)
-    int sc_cfg = -1;                 // scan kernel launch shape (screened default-grid kernels): -1 = auto, 0 = 896 thr x 3 loads, 1 = 768x3, 2 = 1024x2
+    int sc_cfg = -1;                 // scan kernel launch shape (screened default-grid kernels): -1 = auto, 0 = 768 thr x 6 loads, 1 = 768x3, 2 = 1024x2
     int sc_split = -1;               // scan kernel: -1 auto, 0 never split scans into items, 1 always
     int sc_item_points = 131072;     // scan kernel: target points per work item when scans are split
     void *sync_buf = nullptr;        // scan kernel: work-item cursor, per-scan retire counters, item table

@@ -150,22 +150,25 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     const bool split = sc_shape_ok && want_split && split_items < 0x7fff0000LL;
     const bool defgrid = dsc::is_default_grid(cfg) && ctx->no_defgrid == 0;
     // launch shape (threads x 128-bit loads per thread per register set); shapes other than 2 exist for the screened
-    // default-grid kernels only.  More threads = more warps to hide the load latency with and more bytes in flight per
-    // register set, but fewer registers per thread: 896 x 3 (72 registers, nothing spilled on the streaming path) beats
-    // 768 x 3 (80) by 1.5 %, 1024 x 3 / 1024 x 2 (64, spills in the loop) lose 8-10 % (profiles/r2_notes.md, r2n).
-    // Split items reduce with RED.MAX on a grid shared by several CTAs and prefer 768 x 3 (dense2m: 0.58 ms vs 0.71 ms).
+    // default-grid kernels only.  ptxas keeps the loads of both register sets on one scoreboard, so one set is in flight
+    // while the other is processed: the bytes in flight are the size of a set, and the biggest set that still leaves
+    // 24 warps and spills nothing wins -- 768 x 6 (80 registers, 72 KB per set) 1.770 ms, 768 x 5 1.778, 896 x 4 1.789,
+    // 768 x 4 1.794, 896 x 3 1.820, 768 x 3 1.838, 640 x 6 1.808, 896 x 5 (spills) 1.83 (profiles/r2_notes.md, r2q-r2s).
+    // Split items reduce with RED.MAX on a grid shared by several CTAs and prefer 768 x 3 (dense2m: 0.575 ms vs 0.627 ms
+    // for 768 x 4 and 0.71 ms for 896 x 3).
     int shape = (cfg.fast_ok && defgrid) ? (ctx->sc_cfg >= 0 ? ctx->sc_cfg : (split ? 1 : 0)) : 2;   // the generic kernels are 1024 x 2
-#ifdef SC_EXTRA_SHAPES                            // A/B builds: 640 x 3, 512 x 4, 512 x 3, 1024 x 3, 832 x 3
+#ifdef SC_EXTRA_SHAPES                            // A/B builds: 896 x 3, 768 x 5, 896 x 4, 1024 x 3, 640 x 6
     if (shape < 0 || shape > 7) shape = 0;
-    const int nthreads = shape == 0 ? 896 : shape == 1 ? 768 : shape == 3 ? 640 : shape == 7 ? 832 : (shape == 4 || shape == 5) ? 512 : 1024;
+    const int nthreads = (shape == 3 || shape == 5) ? 896 : shape == 7 ? 640 : (shape == 2 || shape == 6) ? 1024 : 768;
 #else
     if (shape != 1 && shape != 2) shape = 0;
-    const int nthreads = shape == 0 ? 896 : shape == 1 ? 768 : 1024;
+    const int nthreads = shape == 2 ? 1024 : 768;
 #endif
     const size_t row_bytes = (size_t)p->num_sector * 4;
     const size_t q_bytes = cfg.fast_ok ? (size_t)SCQ_WARP_BYTES * (nthreads / 32) : 0;       // per-warp exact-path queues
-    // Resident rows.  Shared memory and L1 share 256 KB per SM; beyond the 196 KB carve-out step (164 KB for the
-    // 1024-thread shapes) the streaming loads starve (profiles/r1_notes.md: 60 rows 1.99 ms, 64 rows 2.14 ms).
+    // Resident rows.  Shared memory and L1 share 256 KB per SM; beyond the 196 KiB carve-out step the streaming loads
+    // starve (profiles/r1_notes.md: 60 rows 1.99 ms, 64 rows 2.14 ms; the 1024-thread shapes too: 49 rows 1.90 ms,
+    // 58 rows 1.86 ms, r2p).
     // Split items have no second pass -- every non-resident point is a RED.MAX on a grid that 16 CTAs share --
     // and want every row they can get (dense2m: 62 rows 0.62 ms, 72 rows 0.53 ms).
 #if SC_ASYNC
@@ -176,7 +179,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     const size_t sc_max = sc_budget;
 #else
     const size_t stg_bytes = 0;
-    const size_t sc_budget = split ? ctx->smem_optin : (size_t)(nthreads < 1024 ? 196 : 164) * 1024 - 1024 - 256 - q_bytes;
+    const size_t sc_budget = split ? ctx->smem_optin : (size_t)196 * 1024 - 1024 - 256 - q_bytes;
     const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
 #endif
     int ns = (int)((sc_budget < sc_max ? sc_budget : sc_max) / row_bytes);
@@ -278,11 +281,11 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     } while (0)
 #ifdef SC_EXTRA_SHAPES
 #define SC_EXTRA_LAUNCH(V, H)                                                                                   \
-        else if (shape == 3) SC_LAUNCH3(true, V, H, 3, 640, true);                                              \
-        else if (shape == 4) SC_LAUNCH3(true, V, H, 4, 512, true);                                              \
-        else if (shape == 5) SC_LAUNCH3(true, V, H, 3, 512, true);                                              \
+        else if (shape == 3) SC_LAUNCH3(true, V, H, 3, 896, true);                                              \
+        else if (shape == 4) SC_LAUNCH3(true, V, H, 5, 768, true);                                              \
+        else if (shape == 5) SC_LAUNCH3(true, V, H, 4, 896, true);                                              \
         else if (shape == 6) SC_LAUNCH3(true, V, H, 3, 1024, true);                                             \
-        else if (shape == 7) SC_LAUNCH3(true, V, H, 3, 832, true);
+        else if (shape == 7) SC_LAUNCH3(true, V, H, 6, 640, true);
 #else
 #define SC_EXTRA_LAUNCH(V, H)
 #endif
@@ -291,7 +294,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         if (shape == 1) SC_LAUNCH3(true, V, H, 3, 768, true);                                                   \
         else if (shape == 2) SC_LAUNCH3(true, V, H, 2, 1024, true);                                             \
         SC_EXTRA_LAUNCH(V, H)                                                                                   \
-        else SC_LAUNCH3(true, V, H, 3, 896, true);                                                              \
+        else SC_LAUNCH3(true, V, H, 6, 768, true);                                                              \
     } while (0)
         if (cfg.fast_ok && defgrid) {
             if (p->variant == 0) { if (full) SC_LAUNCH_DEF(0, true); else SC_LAUNCH_DEF(0, false); }

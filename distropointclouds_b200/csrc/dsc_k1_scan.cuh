@@ -44,6 +44,16 @@ constexpr int SC_THREADS = 1024;
 #ifndef SC_VOTE_POINT
 #define SC_VOTE_POINT 1               // 1: one screen-failure vote per point; 0: one per register set
 #endif
+#ifndef SC_UT
+#define SC_UT 2                       // loads per thread in the masked register sets of an item's ragged tail (3 spills in the loop)
+#endif
+#ifndef SC_FU
+#define SC_FU 1                       // 128-bit groups of keys read per thread before the first is decoded in the write-out
+                                      // (1 = the plain loop; 2 / 4 measured 0.4 % / 1.4 % slower, r2p)
+#endif
+#ifndef SC_BAND_BRANCHY
+#define SC_BAND_BRANCHY 0
+#endif
 #ifndef SC_LU
 #define SC_LU 4                       // 128-bit spill-list loads in flight per lane in pass 2
 #endif
@@ -171,6 +181,18 @@ __device__ __forceinline__ bool sc_counts(const float zv)
     return FULL ? (zv == zv) : (zv > 0.0f);
 }
 
+// one real use of every intensity word of a register set (see SC_TOK in k1_scan): lop3 over three words at a time
+template <int U>
+__device__ __forceinline__ uint32_t sc_tok_set(const float4 (&s)[U])
+{
+    uint32_t t = 0u;
+#pragma unroll
+    for (int u = 0; u + 2 < U; u += 3) t ^= sc_tok3(s[u].w, s[u + 1].w, s[u + 2].w);
+    if (U % 3 == 2) t ^= sc_tok2(s[U - 2].w, s[U - 1].w);
+    if (U % 3 == 1) t ^= __float_as_uint(s[U - 1].w);
+    return t;
+}
+
 // Fold one binned point into the key grid.  Called warp-uniformly; `valid` masks lanes without a (counting) point.
 //   resident cell      LDS pre-check + ATOMS.MAX
 //   any other cell     SPILL: appended to the warp's spill list (`gbase` = the launch's spill buffer, `goff` = the warp's
@@ -264,7 +286,8 @@ __device__ __forceinline__ void sc_park(const ExactArgs *ea, const float4 v, con
     }
 }
 
-// One register set -- U points per lane -- called warp-uniformly (`active` masks lanes past the end of the item).
+// One register set -- U points per lane -- called warp-uniformly; the lane's first `mine` points exist (all U in the
+// streaming loop, fewer in the item's last, ragged set).
 // Point by point: screen, commit; then ONE vote per set for the points that failed the screen.
 // (SC_BATCH = 1 screens the U points first as one branch-free block, so that ptxas interleaves the U dependent chains,
 // and commits afterwards: better ILP per warp, but the U (cell, key, valid) triples stay live, predicates get packed
@@ -273,7 +296,7 @@ __device__ __forceinline__ void sc_park(const ExactArgs *ea, const float4 v, con
 // `qoff`: byte offset of the exact-path queues from the rows; the warp's own queue address and the scan's counter block
 // are only formed on the rare paths.  STATS = false: no per-scan counters are kept at all (stats == NULL).
 template <int VARIANT, bool FULL, bool DEF, bool SPILL, bool STATS, int U>
-__device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, const float4 (&v)[U], const bool active,
+__device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, const float4 (&v)[U], const int mine,
                                        uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped, unsigned long long *__restrict__ stats,
                                        const int scan, const SmemRows sm, const uint32_t qoff, unsigned &qcount,
                                        const unsigned lt, const uint32_t wtok = 0u)
@@ -289,6 +312,7 @@ __device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, c
     for (int u = 0; u < U; ++u) {
         int ring, sector;
         bool beyond;
+        const bool active = u < mine;
         bool ok = dsc::screened_core_t<DEF>(cfg, v[u].x, v[u].y, 0.0f, 0.0f, &ring, &sector, &beyond);
         if (VARIANT == 1) ok = ok && (fabsf(v[u].z) < INFINITY);    // finite mask (scan_context_node.py:115)
         bool take = ok && active;
@@ -403,13 +427,25 @@ __device__ __forceinline__ float4 sc_decode4(const uint4 q)
     return f;
 }
 
-// decode `nvec` 128-bit groups of keys from shared memory to floats, re-zeroing the rows
+// decode `nvec` 128-bit groups of keys from shared memory to floats, re-zeroing the rows (SC_FU > 1: that many groups per
+// thread are read before the first is decoded)
 template <int NT, bool FULL>
 __device__ __forceinline__ void sc_flush_rows(uint32_t *__restrict__ srows, float4 *__restrict__ dst, int nvec)
 {
-    for (int i = threadIdx.x; i < nvec; i += NT) {
-        const uint4 q = reinterpret_cast<uint4 *>(srows)[i];
-        reinterpret_cast<uint4 *>(srows)[i] = make_uint4(0, 0, 0, 0);
+    uint4 *const s4 = reinterpret_cast<uint4 *>(srows);
+    int i = threadIdx.x;
+    for (; i + (SC_FU - 1) * NT < nvec; i += SC_FU * NT) {
+        uint4 q[SC_FU];
+#pragma unroll
+        for (int d = 0; d < SC_FU; ++d) q[d] = s4[i + d * NT];
+#pragma unroll
+        for (int d = 0; d < SC_FU; ++d) s4[i + d * NT] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int d = 0; d < SC_FU; ++d) __stcs(dst + i + d * NT, sc_decode4<FULL>(q[d]));
+    }
+    for (; i < nvec; i += NT) {
+        const uint4 q = s4[i];
+        s4[i] = make_uint4(0, 0, 0, 0);
         __stcs(dst + i, sc_decode4<FULL>(q));
     }
 }
@@ -417,8 +453,11 @@ __device__ __forceinline__ void sc_flush_rows(uint32_t *__restrict__ srows, floa
 // fold one spill entry into the band that the shared-memory rows currently stand for: the band is the cell range
 // [lo1, lo1 + n1) followed by [lo2, lo2 + n2) (the remaining rings are the two intervals either side of the window)
 __device__ __forceinline__ void sc_band_entry(const uint32_t cell, const uint32_t key, const uint32_t sbase,
-                                              const uint32_t lo1, const uint32_t n1, const uint32_t lo2, const uint32_t n2)
+                                              const uint32_t lo1, const uint32_t n1, const uint32_t lo2, const uint32_t n2,
+                                              const bool present)
 {
+#if SC_BAND_BRANCHY
+    if (!present) return;
     uint32_t l = cell - lo1;
     if (l >= n1) {
         l = cell - lo2;
@@ -427,6 +466,13 @@ __device__ __forceinline__ void sc_band_entry(const uint32_t cell, const uint32_
     }
     const uint32_t a = sbase + l * 4u;
     if (key > lds_u32(a)) reds_max_u32(a, key);
+#else
+    // branch-free: both interval tests, one predicated LDS pre-check + ATOMS.MAX
+    const uint32_t l1 = cell - lo1, l2 = cell - lo2;
+    const bool in1 = l1 < n1, in2 = l2 < n2;
+    const uint32_t l = in1 ? l1 : l2 + n1;
+    smem_max_if(sbase + l * 4u, key, present && (in1 || in2), 0u);
+#endif
 }
 
 // End of a whole-scan item (this CTA owns the scan): write out the resident rows, then reduce and write out the other
@@ -455,18 +501,18 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
         __syncthreads();                         // the rows are zero again
 #ifndef SC_TIMING_NO_PASS2                       // (timing experiments only: wrong grids)
         // this warp's list: two entries per 128-bit load (L2 hits), SC_LU loads in flight per lane
-        for (int i0 = lane2; i0 < len; i0 += 64 * SC_LU) {
+        for (int i0 = lane2; i0 - lane2 < len; i0 += 64 * SC_LU) {              // warp-uniform trip count
             uint4 q[SC_LU];
 #pragma unroll
-            for (int d = 0; d < SC_LU; ++d)
+            for (int d = 0; d < SC_LU; ++d) {
+                q[d] = make_uint4(0u, 0u, 0u, 0u);
                 if (i0 + 64 * d < len) q[d] = ld_spill2(wseg + i0 + 64 * d);
+            }
 #pragma unroll
             for (int d = 0; d < SC_LU; ++d) {
                 const int i = i0 + 64 * d;
-                if (i < len) {
-                    sc_band_entry(q[d].x, q[d].y, sbase, lo1, n1, lo2, n2);
-                    if (i + 1 < len) sc_band_entry(q[d].z, q[d].w, sbase, lo1, n1, lo2, n2);
-                }
+                sc_band_entry(q[d].x, q[d].y, sbase, lo1, n1, lo2, n2, i < len);
+                sc_band_entry(q[d].z, q[d].w, sbase, lo1, n1, lo2, n2, i + 1 < len);
             }
         }
 #endif
@@ -663,7 +709,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     } while (0)
 #define SC_ONE(vv, act)                                                                                         \
     do {                                                                                                        \
-        if constexpr (FAST) sc_set<VARIANT, FULL, DEF, SPILL, STATS, 1>(cfg, &s_ea, (vv), (act), gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt); \
+        if constexpr (FAST) sc_set<VARIANT, FULL, DEF, SPILL, STATS, 1>(cfg, &s_ea, (vv), (act) ? 1 : 0, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt); \
         else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (vv)[0], (act), gbase, goff, n_clamped, stats, scan, sm, lt); \
     } while (0)
 #pragma unroll
@@ -704,7 +750,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 #define SC_SET(v, tok)                                                                                          \
     do {                                                                                                        \
         if constexpr (FAST) {                                                                                   \
-            sc_set<VARIANT, FULL, DEF, SPILL, STATS, U>(cfg, &s_ea, (v), true, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt, (tok)); \
+            sc_set<VARIANT, FULL, DEF, SPILL, STATS, U>(cfg, &s_ea, (v), U, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt, (tok)); \
         } else {                                                                                                \
             _Pragma("unroll") for (int u = 0; u < U; ++u)                                                       \
                 sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (v)[u], true, gbase, goff, n_clamped, stats, scan, sm, lt); \
@@ -715,38 +761,52 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             // flight -- to instructions of the set processed BEFORE, which then wait for the whole load (write-after-
             // write on the long scoreboard: one POPC held 20 % of all stall samples in profiles/r2d_*) and the register
             // ping-pong is defeated.  The XOR of the words becomes the scratch destination of the first point's LDS.
-#define SC_TOK(s) (U == 4 ? sc_tok3((s)[0].w, (s)[1].w, (s)[2].w) ^ __float_as_uint((s)[U - 1].w) : U == 3 ? sc_tok3((s)[0].w, (s)[1].w, (s)[2].w) : sc_tok2((s)[0].w, (s)[U - 1].w))
+#define SC_TOK(s) sc_tok_set<U>(s)
             if (nfull > 0) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
             }
-            int step = 0;
-            while (step + 1 < nfull) {
+            int left = nfull;                    // register sets still to process (one counter: the loop lives on the
+            while (left >= 2) {                  // edge of its register budget)
 #pragma unroll
                 for (int u = 0; u < U; ++u) b[u] = SC_LD(p + STEP + u * NT);
                 const uint32_t ta = SC_TOK(a);
                 SC_SET(a, ta);
                 p += 2 * STEP;
-                step += 2;
-                if (step < nfull) {
+                left -= 2;
+                if (left > 0) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) a[u] = SC_LD(p + u * NT);
                 }
                 const uint32_t tb = SC_TOK(b);
                 SC_SET(b, tb);
             }
-            if (step < nfull) {
+            if (left > 0) {
                 const uint32_t ta = SC_TOK(a);
                 SC_SET(a, ta);
             }
 #undef SC_TOK
 #undef SC_SET
-            for (int i0 = nfull * STEP; i0 < n; i0 += NT) {       // ragged tail, warp-uniform trip count
-                const bool act = i0 + tid < n;
-                float4 v[1] = {make_float4(1.0f, 1.0f, 0.0f, 0.0f)};
-                if (act) v[0] = SC_LD((uint32_t)p0 + (uint32_t)(i0 + tid));
-                if constexpr (FAST) sc_set<VARIANT, FULL, DEF, SPILL, STATS, 1>(cfg, &s_ea, v, act, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
-                else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, v[0], act, gbase, goff, n_clamped, stats, scan, sm, lt);
+            {   // ragged tail (fewer than STEP points): masked register sets of UT loads, all of a set's loads in flight at once
+                constexpr int UT = U < SC_UT ? U : SC_UT;
+                for (int i0 = nfull * STEP; i0 < n; i0 += UT * NT) {                    // CTA-uniform trip count
+                    const int rem = n - i0;
+                    const int mine = rem > tid ? (rem - tid + NT - 1) / NT : 0;         // >= UT: all of this lane's points exist
+                    const uint32_t pt = (uint32_t)p0 + (uint32_t)(i0 + tid);
+                    float4 t[UT];
+#pragma unroll
+                    for (int u = 0; u < UT; ++u) {
+                        t[u] = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+                        if (u < mine) t[u] = SC_LD(pt + u * NT);
+                    }
+                    if constexpr (FAST) {
+                        sc_set<VARIANT, FULL, DEF, SPILL, STATS, UT>(cfg, &s_ea, t, mine, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < UT; ++u)
+                            sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, t[u], u < mine, gbase, goff, n_clamped, stats, scan, sm, lt);
+                    }
+                }
             }
 #undef SC_LD
 #endif

@@ -98,8 +98,8 @@ float dsc_last_kernel_ms(const dsc_ctx *ctx);
 /* Engine options (debugging / A-B measurements; defaults are the measured best, see profiles/r1_notes.md and profiles/r2_notes.md):
  *   "k1_impl"        0 = auto (k1_scan; generic kernels for 12-byte stride / odd shapes / few small scans),
  *                    1 = generic L2-key kernels only, 3 = k1_scan whenever the shape allows
- *   "sc_cfg"         k1_scan launch shape: -1 = auto (896 threads x 3 loads per register set for whole scans, 768 x 3 when
- *                    scans are cut into work items), 0 = 896 x 3, 1 = 768 x 3, 2 = 1024 x 2
+ *   "sc_cfg"         k1_scan launch shape: -1 = auto (768 threads x 6 loads per register set for whole scans, 768 x 3 when
+ *                    scans are cut into work items), 0 = 768 x 6, 1 = 768 x 3, 2 = 1024 x 2
  *   "sc_smem_rows"   resident ring rows of k1_scan (-1 = as many as the carve-out allows)
  *   "sc_window"      first ring of k1_scan's resident window (-1 = chosen per call by k1_probe from a ring histogram
  *                    of sampled points; the grids never depend on it)
