@@ -198,24 +198,37 @@ __device__ __forceinline__ uint32_t sc_tok_set(const float4 (&s)[U])
 //   any other cell     SPILL: appended to the warp's spill list (`gbase` = the launch's spill buffer, `goff` = the warp's
 //                      write position in it, in entries, advanced for the whole warp; `lt` = %lanemask_lt);
 //                      !SPILL (split items): RED.MAX straight into the scan's key grid (`gbase`)
-template <bool SPILL>
-__device__ __forceinline__ void sc_commit(const uint32_t key, const int cell, const bool valid, const SmemRows sm, uint32_t *const gbase,
-                                          uint32_t &goff, const unsigned lt, const uint32_t w = 0u)
+// shared-memory part of a commit; returns "this lane's point belongs to a ring that is not resident"
+__device__ __forceinline__ bool sc_commit_rows(const uint32_t key, const int cell, const bool valid, const SmemRows sm, const uint32_t w)
 {
     const int rel = cell - sm.c0;
     const bool win = (uint32_t)rel < (uint32_t)sm.lim;                          // rings r0 .. r0+ns-2
     const bool res = win || cell >= sm.last;
     const int local = win ? rel : cell + sm.shift;                              // clamp ring -> row ns-1
     smem_max_if(sm.base + (uint32_t)local * 4u, key, valid && res, w);
-    if constexpr (SPILL) {
-        const bool sp = valid && !res;
-        const unsigned m = __ballot_sync(0xffffffffu, sp);
+    return valid && !res;
+}
+// append the non-resident points of the warp (`sp` lanes) to its spill list; called warp-uniformly
+__device__ __forceinline__ void sc_spill(const bool sp, const uint32_t key, const int cell, uint32_t *const gbase, uint32_t &goff,
+                                         const unsigned lt)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, sp);
 #ifndef SC_TIMING_NO_SPILL                       // (timing experiments only: wrong grids)
-        if (sp) st_spill(reinterpret_cast<uint2 *>(gbase) + (goff + __popc(m & lt)), (uint32_t)cell, key);
+    if (sp) st_spill(reinterpret_cast<uint2 *>(gbase) + (goff + __popc(m & lt)), (uint32_t)cell, key);
 #endif
-        goff += __popc(m);
+    goff += __popc(m);
+}
+template <bool SPILL>
+__device__ __forceinline__ void sc_commit(const uint32_t key, const int cell, const bool valid, const SmemRows sm, uint32_t *const gbase,
+                                          uint32_t &goff, const unsigned lt, const uint32_t w = 0u)
+{
+    const bool sp = sc_commit_rows(key, cell, valid, sm, w);
+    if constexpr (SPILL) {
+        // most warps have no spilling lane (consecutive points of a beam share their rings): one warp-uniform branch
+        // around rank, address and store instead of six predicated instructions
+        if (__any_sync(0xffffffffu, sp)) sc_spill(sp, key, cell, gbase, goff, lt);
     } else {
-        if (valid && !res) red_max_global(gbase + cell, key);
+        if (sp) red_max_global(gbase + cell, key);
     }
 }
 
@@ -333,10 +346,23 @@ __device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, c
 #pragma unroll
     for (int u = 0; u < U; ++u) sc_commit<SPILL>(key[u], cell[u], valid[u], sm, gbase, goff, lt, u == 0 ? wtok : 0u);
 #else
-        sc_commit<SPILL>(sc_key<FULL>(zv), ring * S + sector, take && sc_counts<FULL>(zv), sm, gbase, goff, lt, u == 0 ? wtok : 0u);
 #if SC_VOTE_POINT
-        if (__any_sync(0xffffffffu, slow[u]))    // warp-uniform, rare
-            sc_park<VARIANT, FULL, SPILL, STATS>(ea, v[u], slow[u], gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
+        {   // ONE vote per point for "some lane spills or failed the screen": most warps have neither (consecutive points
+            // of a beam share their rings; 0.3 % of the points fail the screen)
+            const uint32_t key = sc_key<FULL>(zv);
+            const int cell = ring * S + sector;
+            const bool sp = sc_commit_rows(key, cell, take && sc_counts<FULL>(zv), sm, u == 0 ? wtok : 0u);
+            if constexpr (!SPILL) {
+                if (sp) red_max_global(gbase + cell, key);
+            }
+            if (__any_sync(0xffffffffu, (SPILL && sp) || slow[u])) {
+                if constexpr (SPILL) sc_spill(sp, key, cell, gbase, goff, lt);
+                if (__any_sync(0xffffffffu, slow[u]))
+                    sc_park<VARIANT, FULL, SPILL, STATS>(ea, v[u], slow[u], gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
+            }
+        }
+#else
+        sc_commit<SPILL>(sc_key<FULL>(zv), ring * S + sector, take && sc_counts<FULL>(zv), sm, gbase, goff, lt, u == 0 ? wtok : 0u);
 #endif
     }
 #endif
