@@ -210,11 +210,16 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
     __shared__ int s_g, s_alloc, s_left, s_rowA, s_rowC;
     __shared__ volatile int s_ready;             // the grid's base offset has been published (look-back done)
     __shared__ long long s_base;
-    // dynamic: [per-warp staging][row offsets R+1][row buffer positions R][heights zcap][sectors zcap]
+    // dynamic: [per-warp staging][cos S][sin S][ring centres R][row offsets R+1][row buffer positions R][heights zcap][sectors zcap]
     extern __shared__ __align__(16) double k3_smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double *dbuf = k3_smem + (size_t)w * (K3F_STAGE_BYTES / 8);
-    int *s_cnt = reinterpret_cast<int *>(k3_smem + (size_t)K3F_WARPS * (K3F_STAGE_BYTES / 8));
+    // the polar tables live in shared memory for the whole launch: pass C reads two of their entries per point, and from
+    // global memory that was an L1/L2 round trip in front of every DMUL (5 % of the stall samples, profiles/r2j_k3_fused.*)
+    double *s_cos = k3_smem + (size_t)K3F_WARPS * (K3F_STAGE_BYTES / 8);
+    double *s_sin = s_cos + S;
+    double *s_rc = s_sin + S;
+    int *s_cnt = reinterpret_cast<int *>(s_rc + R);
     int *s_pos = s_cnt + (R + 1);
     float *zbuf = reinterpret_cast<float *>(s_pos + R + ((R + 1 + R) & 1));
     unsigned short *jbuf = reinterpret_cast<unsigned short *>(zbuf + zcap);
@@ -223,6 +228,11 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
     uint64_t pol_keep, pol_drop;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
+    for (int i = tid; i < S; i += K3F_THREADS) {
+        s_cos[i] = cosT[i];
+        s_sin[i] = sinT[i];
+    }
+    for (int i = tid; i < R; i += K3F_THREADS) s_rc[i] = rcs[i];
     for (;;) {
         if (tid == 0) {
             s_g = (int)atomicAdd(ticket, 1u);
@@ -327,7 +337,7 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
                 const int rowoff = s_cnt[r];
                 const int count = s_cnt[r + 1] - rowoff;
                 if (count == 0) continue;
-                const double rc = rcs[r];
+                const double rc = s_rc[r];
                 const int idbase = r * S;
                 if (!have_base) {                            // first store of this warp for this grid
                     while (!s_ready) __nanosleep(20);
@@ -349,8 +359,8 @@ k3_fused(const float *__restrict__ grids, int n_grids, int R, int S, int full_he
                     if (lane < m) {
                         const float z = zp[e0];
                         const int j = jp[e0];
-                        dbuf[3 * lane + 0] = __dmul_rn(rc, cosT[j]);   // :58  X = r * cos(theta)
-                        dbuf[3 * lane + 1] = __dmul_rn(rc, sinT[j]);   // :59
+                        dbuf[3 * lane + 0] = __dmul_rn(rc, s_cos[j]);  // :58  X = r * cos(theta)
+                        dbuf[3 * lane + 1] = __dmul_rn(rc, s_sin[j]);  // :59
                         // :66 the offset is removed in the grid's dtype (float32 .npy grids)
                         dbuf[3 * lane + 2] = full_height ? (double)z : (double)__fsub_rn(z, offset_f);
                         id = idbase + j;                               // :74
@@ -636,7 +646,7 @@ extern "C" int dsc_reconstruct_batch(dsc_ctx *ctx, const float *grids, int n_gri
             const int max_ctas = ctx->sm_count * K3F_CTAS_PER_SM;
             const int ctas = n_grids < max_ctas ? n_grids : max_ctas;   // tickets are drawn by running CTAs only: look-back cannot stall
             // shared memory: per-warp staging, the two row tables, and as many compaction entries (6 B) as fit
-            const size_t k3_fixed = (size_t)K3F_WARPS * K3F_STAGE_BYTES + (size_t)(2 * R + 2) * 4 + 16;
+            const size_t k3_fixed = (size_t)K3F_WARPS * K3F_STAGE_BYTES + (size_t)(2 * S + R) * 8 + (size_t)(2 * R + 2) * 4 + 16;
             int zcap = (int)((ctx->smem_optin - 1024 - k3_fixed) / 6) & ~7;
             if (zcap > R * S) zcap = (R * S + 7) & ~7;
             const int k3_smem = (int)(k3_fixed + (size_t)zcap * 6);
