@@ -506,3 +506,28 @@ def test_reconstructor_dense_grids_take_several_compaction_rounds(orc):
                 op, oi = orc.reconstruct(g[i], full_height=full, height_offset=2.0)
                 assert np.array_equal(out[i][1], oi), (full, i)
                 assert np.array_equal(out[i][0], op), (full, i)
+
+
+@pytest.mark.parametrize("shape", [0, 1, 2])
+@pytest.mark.parametrize("split", [0, 1])
+def test_every_launch_shape_of_the_scan_kernel(orc, golden_scans, golden_grids, shape, split):
+    """k1_scan ships three launch shapes for the default grid (768 threads x 6 loads per register set, 768 x 3,
+    1024 x 2; "sc_cfg").  Each one, as whole-scan items and as split items, on the golden scans and on ragged
+    synthetic scans whose tails exercise the masked last register sets (0, 1, a few hundred and a few thousand
+    points past a multiple of the set size), both variants, both height modes: bit-exact against the oracle."""
+    from distropointclouds_b200.engine import Engine
+    rng = np.random.default_rng(100 + shape)
+    sizes = [0, 1, 767, 768, 4607, 4608, 4609, 9216 + 300, 3 * 4608 + 2047, 31000]
+    scans = [golden_scans["000840"], golden_scans["002073"]]
+    scans += [(rng.standard_normal((n, 4)) * [11, 11, 1.5, 1]).astype(np.float32) for n in sizes]
+    with Engine(0) as e:
+        e.set_option("k1_impl", 3)
+        e.set_option("sc_cfg", shape)
+        e.set_option("sc_split", split)
+        for variant in (0, 1):
+            for full in (True, False):
+                op = orc.Params(160, 720, 20.0 if variant == 0 else 80.0, variant, full, 2.0)
+                check_against_oracle(e, orc, scans, op, what=f"shape{shape} split{split} v{variant} full{full}")
+        if shape == 0 and split == 0:
+            got, _, _ = e.build_scans(scans[:2], P())
+            assert np.array_equal(got[0], golden_grids["000840"]) and np.array_equal(got[1], golden_grids["002073"])
