@@ -246,18 +246,24 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             }
         }
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
-        DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, sync_bytes, st));
-        // resident window: ring histogram of sampled points -> first ring r0 (device-side; no host round trip)
-        if (!ctx->probe) DSC_CUDA(ctx, cudaMalloc(&ctx->probe, (PROBE_MAXR + 4) * sizeof(unsigned int)));
+        // resident window: ring histogram of sampled points -> first ring r0 (device-side; no host round trip).  The
+        // probe leaves its histogram zeroed for the next call and resets the work cursor of the launch that follows,
+        // so the common whole-scan call is two launches and no memset.
+        if (!ctx->probe) {
+            DSC_CUDA(ctx, cudaMalloc(&ctx->probe, (PROBE_MAXR + 4) * sizeof(unsigned int)));
+            DSC_CUDA(ctx, cudaMemsetAsync(ctx->probe, 0, (PROBE_MAXR + 4) * sizeof(unsigned int), st));
+        }
         unsigned int *probe = (unsigned int *)ctx->probe;
         int *window = (int *)(probe + PROBE_MAXR + 2);
-        DSC_CUDA(ctx, cudaMemsetAsync(probe, 0, (PROBE_MAXR + 4) * sizeof(unsigned int), st));
-        if (total_pts > 0 && p->num_ring <= PROBE_MAXR && ns < p->num_ring && ctx->sc_window < 0) {
+        const bool run_probe = total_pts > 0 && p->num_ring <= PROBE_MAXR && ns < p->num_ring && ctx->sc_window < 0;
+        if (!run_probe || sync_bytes > 16) DSC_CUDA(ctx, cudaMemsetAsync(cursor, 0, sync_bytes, st));
+        if (run_probe) {
             k1_probe<<<PROBE_BLOCKS, PROBE_THREADS, 0, st>>>(pts, h_offsets[0], total_pts, (float)(p->num_ring / p->max_length),
-                                                             p->num_ring, ns - 1, probe, window);
+                                                             p->num_ring, ns - 1, probe, window, cursor);
             if ((rc = dsc_check_launch(ctx, "k1_probe"))) return rc;
-        } else if (ctx->sc_window > 0) {                 // A/B override
-            const int w = ctx->sc_window <= p->num_ring - ns ? ctx->sc_window : (p->num_ring - ns > 0 ? p->num_ring - ns : 0);
+        } else {                                         // no probe: window at ring 0, or the A/B override
+            const int w = ctx->sc_window <= 0 ? 0
+                        : ctx->sc_window <= p->num_ring - ns ? ctx->sc_window : (p->num_ring - ns > 0 ? p->num_ring - ns : 0);
             DSC_CUDA(ctx, cudaMemcpyAsync(window, &w, sizeof(int), cudaMemcpyHostToDevice, st));
         }
         unsigned long long *stp = (unsigned long long *)stats;

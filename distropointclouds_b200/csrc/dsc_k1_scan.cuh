@@ -869,16 +869,20 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 // Ring histogram of PROBE_BLOCKS * PROBE_THREADS * PROBE_PPT pseudo-randomly sampled points of the batch; the last
 // block to finish picks the start ring r0 of the window of `nwin` rings that holds the most samples (ring R-1, the
 // clamp ring, is resident anyway and not part of the search) and writes it to *window.  A heuristic only: the grids
-// do not depend on r0.  probe[] = ring histogram [R], then the finished-blocks counter; zeroed before the launch.
+// do not depend on r0.  probe[] = ring histogram [R], then the finished-blocks counter: zero when the kernel starts
+// (zeroed once when the buffer is allocated) and zero again when it ends -- the last block cleans up after itself, and
+// block 0 resets the work cursor of the k1_scan launch that follows, so a call needs no memset of its own.
 constexpr int PROBE_BLOCKS = 32, PROBE_THREADS = 256, PROBE_PPT = 8, PROBE_MAXR = 4096;
 
 __global__ void __launch_bounds__(PROBE_THREADS)
 k1_probe(const uint8_t *__restrict__ pts, const int64_t first, const int64_t total, const float inv_gap_ring, const int R,
-         const int nwin, unsigned int *__restrict__ probe, int *__restrict__ window)
+         const int nwin, unsigned int *__restrict__ probe, int *__restrict__ window, unsigned int *__restrict__ cursor)
 {
     __shared__ unsigned int sh[PROBE_MAXR];
+    __shared__ unsigned long long s_best[PROBE_THREADS / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0 && cursor) *cursor = 0u;
     for (int i = tid; i < R; i += PROBE_THREADS) sh[i] = 0u;
     __syncthreads();
     const float4 *p4 = reinterpret_cast<const float4 *>(pts) + first;
@@ -901,17 +905,29 @@ k1_probe(const uint8_t *__restrict__ pts, const int64_t first, const int64_t tot
     }
     __syncthreads();
     if (!s_last) return;
-    for (int i = tid; i < R; i += PROBE_THREADS) sh[i] = __ldcg(probe + i);
+    for (int i = tid; i < R; i += PROBE_THREADS) {
+        sh[i] = __ldcg(probe + i);
+        probe[i] = 0u;                                            // leave the histogram clean for the next call
+    }
+    if (tid == 0) probe[R] = 0u;
+    __syncthreads();
+    // windows [s, s + nwin) below the clamp ring: every thread sums its candidates, the best (count, lowest start) wins
+    unsigned long long best = 0ull;                               // (count << 32) | ~start: max = most samples, lowest start
+    for (int s0 = tid; s0 + nwin <= R - 1; s0 += PROBE_THREADS) {   // (host guarantees nwin <= R - 2: s0 = 0 is a candidate)
+        unsigned int c = 0;
+        for (int i = s0; i < s0 + nwin; ++i) c += sh[i];
+        const unsigned long long cand = ((unsigned long long)c << 32) | (unsigned int)~s0;
+        best = cand > best ? cand : best;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o > best ? o : best;
+    }
+    if ((tid & 31) == 0) s_best[tid >> 5] = best;
     __syncthreads();
     if (tid == 0) {
-        unsigned int cur = 0, best;
-        for (int i = 0; i < nwin; ++i) cur += sh[i];
-        best = cur;
-        int r0 = 0;
-        for (int s = 1; s + nwin <= R - 1; ++s) {                 // windows [s, s + nwin) below the clamp ring
-            cur += sh[s + nwin - 1] - sh[s - 1];
-            if (cur > best) { best = cur; r0 = s; }
-        }
-        *window = r0;
+        for (int w = 1; w < PROBE_THREADS / 32; ++w) best = s_best[w] > best ? s_best[w] : best;
+        *window = (int)~(unsigned int)(best & 0xffffffffull);
     }
 }
