@@ -190,7 +190,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     // per band: grids with very many rings for their row size go to the generic path instead
     const int bands = ns >= 2 ? (p->num_ring - ns + ns - 1) / ns : 0x7fffffff;
     // (whole-scan items address their spill lists with 32-bit entry indices: sm_count regions of max_pts entries)
-    const bool spill_ok = (int64_t)ctx->sm_count * (max_pts + nthreads) < 0xffff0000LL;
+    const bool spill_ok = (int64_t)ctx->sm_count * (max_pts + 2 * nthreads) < 0xffff0000LL;
     const bool sc_ok = sc_shape_ok && ns >= 2 && (split || (bands <= 8 && spill_ok)) &&
                        (split || ctx->k1_impl == 3 || n_scans >= ctx->sm_count / 2);
     if (sc_ok) {
@@ -233,7 +233,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             if ((rc = dsc_reserve_sync(ctx, 256))) return rc;
             // spill lists: one region per CTA, big enough for every point of the largest scan (only the part that
             // is used -- the points outside the resident rings, ~15 % on KITTI-like scans -- is ever touched)
-            spill_cap = (size_t)((max_pts + nthreads - 1) / nthreads) * (size_t)nthreads;
+            spill_cap = (size_t)((max_pts + nthreads - 1) / nthreads + 1) * (size_t)nthreads;     // (+1: see sc_drain)
             if (spill_cap < (size_t)nthreads) spill_cap = (size_t)nthreads;
             const size_t need = SC_SLOT ? (size_t)ctx->sm_count * cells * 4 : (size_t)ctas * spill_cap * sizeof(uint2);
             if (need > ctx->spill_bytes) {

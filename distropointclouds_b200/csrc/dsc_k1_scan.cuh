@@ -249,22 +249,29 @@ __device__ __noinline__ uint2 sc_exact_queued(uint32_t qaddr, const ExactArgs *_
     return b;
 }
 
-// run the exact chain for the queue entries [first, first + count) of this warp (count <= 32) and commit them
+// run the exact chain for one queue entry per lane (`qaddr`, lanes with `mine`) and commit the results; warp-uniform
+template <int VARIANT, bool FULL, bool SPILL>
+__device__ __forceinline__ void sc_exact_lanes(const uint32_t qaddr, const bool mine, const ExactArgs *ea, uint32_t *const gbase,
+                                               uint32_t &goff, unsigned &n_clamped, unsigned long long *__restrict__ st,
+                                               const SmemRows sm, const unsigned lt)
+{
+    uint2 b = make_uint2((uint32_t)dsc::PT_NONFINITE << 27, 0u);
+    __syncwarp();
+    if (mine) b = sc_exact_queued<VARIANT, FULL>(qaddr, ea, st);
+    __syncwarp();
+    const int status = (int)(b.x >> 27);
+    n_clamped += (mine && status == dsc::PT_CLAMPED) ? 1u : 0u;
+    const float zv = __uint_as_float(b.y);
+    sc_commit<SPILL>(sc_key<FULL>(zv), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED && sc_counts<FULL>(zv), sm, gbase, goff, lt);
+}
+// ... for the queue entries [first, first + count) of this warp (count <= 32)
 template <int VARIANT, bool FULL, bool SPILL>
 __device__ __forceinline__ void sc_exact_batch(const uint32_t queue, const unsigned first, const unsigned count,
                                                const ExactArgs *ea, uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped,
                                                unsigned long long *__restrict__ st, const SmemRows sm, const unsigned lt)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const bool mine = lane < count;
-    uint2 b = make_uint2((uint32_t)dsc::PT_NONFINITE << 27, 0u);
-    __syncwarp();
-    if (mine) b = sc_exact_queued<VARIANT, FULL>(queue + (first + lane) * 4u, ea, st);
-    __syncwarp();
-    const int status = (int)(b.x >> 27);
-    n_clamped += (mine && status == dsc::PT_CLAMPED) ? 1u : 0u;
-    const float zv = __uint_as_float(b.y);
-    sc_commit<SPILL>(sc_key<FULL>(zv), (int)(b.x & 0x7ffffffu), mine && status <= dsc::PT_CLAMPED && sc_counts<FULL>(zv), sm, gbase, goff, lt);
+    sc_exact_lanes<VARIANT, FULL, SPILL>(queue + (first + lane) * 4u, lane < count, ea, gbase, goff, n_clamped, st, sm, lt);
 }
 
 // Park the points that failed the screen (`slow` lanes) in the warp's exact-path queue; run the exact chain when 32 wait.
@@ -402,17 +409,48 @@ __device__ __forceinline__ void sc_point_exact(const ExactArgs *ea, const float4
     sc_commit<SPILL>(sc_key<FULL>(zv), (int)(b.x & 0x7ffffffu), active && status <= dsc::PT_CLAMPED && sc_counts<FULL>(zv), sm, gbase, goff, lt);
 }
 
-// end of item: the queue's remaining entries (fewer than 32)
-template <int VARIANT, bool FULL, bool SPILL>
+// End of item: the queues' remaining entries (fewer than 32 per warp).  Each warp draining its own ~13 entries would run
+// the ~300-instruction exact chain 24 times per scan, half empty -- 70 % of all its executions.  Groups of G warps pool
+// what they have left instead (a named barrier over the group, counts through shared memory) and deal the pooled
+// entries out in batches of 32, round-robin: ceil(total / 32) executions per group, still in parallel.
+// A warp may so commit up to 32 points that it did not stream itself: its spill list has one more row of 32 entries
+// than its own points need (see `seg` in k1_scan).
+template <int VARIANT, bool FULL, bool SPILL, int NT>
 __device__ __forceinline__ void sc_drain(const ExactArgs *ea, uint32_t *const gbase, uint32_t &goff, unsigned &n_clamped,
                                          unsigned long long *__restrict__ st, const SmemRows sm, const uint32_t qoff,
-                                         unsigned &qcount, const unsigned lt)
+                                         unsigned &qcount, const unsigned lt, int *__restrict__ s_qcnt)
 {
-    if (qcount) {                                // warp-uniform
-        const uint32_t queue = sm.base + qoff + (threadIdx.x >> 5) * SCQ_WARP_BYTES;
-        sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gbase, goff, n_clamped, st, sm, lt);
-        qcount = 0;
+    constexpr int W = NT / 32;
+    constexpr int G = (W % 4 == 0) ? 4 : (W % 2 == 0) ? 2 : 1;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if constexpr (G == 1) {
+        if (qcount) {                            // warp-uniform
+            const uint32_t queue = sm.base + qoff + warp * SCQ_WARP_BYTES;
+            sc_exact_batch<VARIANT, FULL, SPILL>(queue, 0u, qcount, ea, gbase, goff, n_clamped, st, sm, lt);
+        }
+    } else {
+        const unsigned g = warp / G, wi = warp % G;
+        if (lane == 0) s_qcnt[warp] = (int)qcount;
+        asm volatile("bar.sync %0, %1;" ::"r"(1u + g), "r"((unsigned)(G * 32)) : "memory");    // barrier 0 is __syncthreads'
+        int c[G], total = 0;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            c[k] = s_qcnt[g * G + k];
+            total += c[k];
+        }
+        const uint32_t gq = sm.base + qoff + g * G * SCQ_WARP_BYTES;            // the group's first queue
+        for (int b = (int)wi; b * 32 < total; b += G) {                         // group-uniform bounds, warp-uniform trip count
+            int j = b * 32 + (int)lane;
+            const bool mine = j < total;
+            int q = 0;
+#pragma unroll
+            for (int k = 0; k + 1 < G; ++k)
+                if (q == k && j >= c[k]) { j -= c[k]; q = k + 1; }
+            sc_exact_lanes<VARIANT, FULL, SPILL>(gq + (uint32_t)q * SCQ_WARP_BYTES + (uint32_t)j * 4u, mine, ea, gbase, goff, n_clamped,
+                                                 st, sm, lt);
+        }
     }
+    qcount = 0;
 }
 
 // work item -> (scan, first point, point count, parts of the scan, key grid)
@@ -657,6 +695,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ int s_next[2];
     __shared__ int s_last;
+    __shared__ int s_qcnt[NT / 32];
     __shared__ ExactArgs s_ea;
     const int tid = threadIdx.x;
     const int R = DEF ? dsc::defgrid::R : cfg.R, S = DEF ? dsc::defgrid::S : cfg.S;
@@ -706,7 +745,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             } else {
                 // the write position counts entries from the start of the launch's spill buffer (host guarantees
                 // gridDim.x * spill_cap < 2^32): the store address is one multiply-add away from it
-                const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;       // most points one warp can see
+                const unsigned seg = (unsigned)((n + NT - 1) / NT + 1) * 32u;   // most entries one warp can append (see sc_drain)
                 gbase = reinterpret_cast<uint32_t *>(spill);
                 goff = blockIdx.x * (uint32_t)spill_cap + (uint32_t)(tid >> 5) * seg;
             }
@@ -837,7 +876,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
 #undef SC_LD
 #endif
             unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
-            if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL>(&s_ea, gbase, goff, n_clamped, st, sm, qoff, qcount, lt);
+            if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL, NT>(&s_ea, gbase, goff, n_clamped, st, sm, qoff, qcount, lt, s_qcnt);
             if (STATS) {
                 const unsigned c = __reduce_add_sync(0xffffffffu, n_clamped);
                 if ((tid & 31) == 0 && c) atomicAdd(st + 3, (unsigned long long)c);
@@ -855,7 +894,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             } else if constexpr (SC_SLOT) {
                 sc_finish_slot<NT, FULL, SC_DU>(srows, gbase, out + (size_t)scan * cells, ns, r0, R, S);
             } else {
-                const unsigned seg = (unsigned)((n + NT - 1) / NT) * 32u;
+                const unsigned seg = (unsigned)((n + NT - 1) / NT + 1) * 32u;
                 const uint32_t w0 = blockIdx.x * (uint32_t)spill_cap + (uint32_t)(tid >> 5) * seg;
                 sc_finish_scan<NT, FULL>(srows, sm.base, out + (size_t)scan * cells, ns, r0, R, S, spill + w0, (int)(goff - w0));
             }
