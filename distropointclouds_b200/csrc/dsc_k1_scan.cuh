@@ -54,6 +54,9 @@ constexpr int SC_THREADS = 1024;
 #ifndef SC_BAND_BRANCHY
 #define SC_BAND_BRANCHY 0
 #endif
+#ifndef SC_LIST_PIPE
+#define SC_LIST_PIPE 0                // 1 (A/B builds): the band passes request list batch k+1 before folding batch k in, and the first
+#endif                                // batch of a band before the write-out in front of it -- 2.6 % SLOWER (1.811 vs 1.765 ms, r2ac)
 #ifndef SC_LU
 #define SC_LU 4                       // 128-bit spill-list loads in flight per lane in pass 2
 #endif
@@ -549,6 +552,21 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
     const int rowvec = S >> 2;
     float4 *oq = reinterpret_cast<float4 *>(out_scan);
     const int lane2 = 2 * (int)(threadIdx.x & 31u);
+    // this warp's list is read two entries per 128-bit load (L2 hits), SC_LU loads per lane and batch
+    auto load_batch = [&](uint4(&q)[SC_LU], const int i0) {
+#pragma unroll
+        for (int d = 0; d < SC_LU; ++d) {
+            q[d] = make_uint4(0u, 0u, 0u, 0u);
+            if (i0 + 64 * d < len) q[d] = ld_spill2(wseg + i0 + 64 * d);
+        }
+    };
+#if SC_LIST_PIPE
+    // The first batch of a band is requested BEFORE the write-out and the barrier in front of the band (the warp's own
+    // list is complete: only its own lanes append to it), and batch k+1 before batch k is folded in.  Measured slower.
+    uint4 q[SC_LU];
+    __syncwarp();
+    load_batch(q, lane2);
+#endif
     __syncthreads();                             // every shared-memory atomic and every list store of the item is done
     // resident rows: rings r0 .. r0+ns-2, and the clamp ring R-1 kept in row ns-1
     sc_flush_rows<NT, FULL>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
@@ -564,21 +582,28 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
         const uint32_t lo2 = (uint32_t)ring2 * (uint32_t)S, n2 = (uint32_t)rows2 * (uint32_t)S;
         __syncthreads();                         // the rows are zero again
 #ifndef SC_TIMING_NO_PASS2                       // (timing experiments only: wrong grids)
-        // this warp's list: two entries per 128-bit load (L2 hits), SC_LU loads in flight per lane
         for (int i0 = lane2; i0 - lane2 < len; i0 += 64 * SC_LU) {              // warp-uniform trip count
+#if SC_LIST_PIPE
+            uint4 nq[SC_LU];
+            load_batch(nq, i0 + 64 * SC_LU);                                     // (nothing is requested past the end of the list)
+#else
             uint4 q[SC_LU];
-#pragma unroll
-            for (int d = 0; d < SC_LU; ++d) {
-                q[d] = make_uint4(0u, 0u, 0u, 0u);
-                if (i0 + 64 * d < len) q[d] = ld_spill2(wseg + i0 + 64 * d);
-            }
+            load_batch(q, i0);
+#endif
 #pragma unroll
             for (int d = 0; d < SC_LU; ++d) {
                 const int i = i0 + 64 * d;
                 sc_band_entry(q[d].x, q[d].y, sbase, lo1, n1, lo2, n2, i < len);
                 sc_band_entry(q[d].z, q[d].w, sbase, lo1, n1, lo2, n2, i + 1 < len);
             }
+#if SC_LIST_PIPE
+#pragma unroll
+            for (int d = 0; d < SC_LU; ++d) q[d] = nq[d];
+#endif
         }
+#if SC_LIST_PIPE
+        if (b0 + ns < nv) load_batch(q, lane2);  // first batch of the next band, in flight during this band's write-out
+#endif
 #endif
         __syncthreads();
         sc_flush_rows<NT, FULL>(srows, oq + (size_t)b0 * rowvec, rows1 * rowvec);
