@@ -171,17 +171,8 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
     // 58 rows 1.86 ms, r2p).
     // Split items have no second pass -- every non-resident point is a RED.MAX on a grid that 16 CTAs share --
     // and want every row they can get (dense2m: 62 rows 0.62 ms, 72 rows 0.53 ms).
-#if SC_ASYNC
-    // the stream is staged through shared memory (SC_NG groups of one point per thread) and no longer lands in L1:
-    // rows + queues + staging may take everything the SM offers
-    const size_t stg_bytes = (size_t)SC_NG * nthreads * 16;
-    const size_t sc_budget = ctx->smem_optin - 1024 - q_bytes - stg_bytes;
-    const size_t sc_max = sc_budget;
-#else
-    const size_t stg_bytes = 0;
     const size_t sc_budget = split ? ctx->smem_optin : (size_t)196 * 1024 - 1024 - 256 - q_bytes;
     const size_t sc_max = ctx->smem_optin - 1024 - q_bytes;
-#endif
     int ns = (int)((sc_budget < sc_max ? sc_budget : sc_max) / row_bytes);
     if (ctx->sc_smem_rows >= 0) ns = ctx->sc_smem_rows;                          // A/B override
     if ((size_t)ns * row_bytes > sc_max) ns = (int)(sc_max / row_bytes);
@@ -235,14 +226,13 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
             // is used -- the points outside the resident rings, ~15 % on KITTI-like scans -- is ever touched)
             spill_cap = (size_t)((max_pts + nthreads - 1) / nthreads + 1) * (size_t)nthreads;     // (+1: see sc_drain)
             if (spill_cap < (size_t)nthreads) spill_cap = (size_t)nthreads;
-            const size_t need = SC_SLOT ? (size_t)ctx->sm_count * cells * 4 : (size_t)ctas * spill_cap * sizeof(uint2);
+            const size_t need = (size_t)ctas * spill_cap * sizeof(uint2);
             if (need > ctx->spill_bytes) {
                 if (ctx->spill) { DSC_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->spill); }
                 ctx->spill = nullptr;
                 ctx->spill_bytes = 0;
                 DSC_CUDA(ctx, cudaMalloc(&ctx->spill, need));
                 ctx->spill_bytes = need;
-                if (SC_SLOT) DSC_CUDA(ctx, cudaMemsetAsync(ctx->spill, 0, need, st));     // key slots: left zeroed by the kernel
             }
         }
         unsigned int *cursor = (unsigned int *)ctx->sync_buf;
@@ -268,7 +258,7 @@ static int build_device(dsc_ctx *ctx, const dsc_params *p, const uint8_t *pts, c
         }
         unsigned long long *stp = (unsigned long long *)stats;
         const bool full = p->full_height != 0;
-        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes + stg_bytes;
+        const size_t sc_smem = (size_t)ns * row_bytes + q_bytes;
 #define SC_LAUNCH5(F, V, H, U, NT, D, SP, ST)                                                                   \
     do {                                                                                                        \
         DSC_CUDA(ctx, cudaFuncSetAttribute(k1_scan<F, V, H, U, NT, D, SP, ST>,                                  \

@@ -26,37 +26,9 @@ constexpr int SC_THREADS = 1024;
 #ifndef SC_DU
 #define SC_DU 4                       // 128-bit L2 loads in flight per thread in the split-mode decode
 #endif
-#ifndef SC_SLOT
-#define SC_SLOT 0                     // 1 (A/B builds): whole-scan items reduce the non-resident rings with RED.MAX on a private
-#endif                                // L2 key slot per CTA and read it back (the round-1 form) instead of spill lists + bands
-#ifndef SC_BATCH
-#define SC_BATCH 0                    // 1 (A/B builds): screen the U points of a register set first, then commit them (slower: r2k)
-#endif
-#ifndef SC_NO_PRECHECK
-#define SC_NO_PRECHECK 0
-#endif
-#ifndef SC_ASYNC
-#define SC_ASYNC 0                    // 1: the stream is staged through shared memory with cp.async (see k1_scan)
-#endif
-#ifndef SC_NG
-#define SC_NG 4                       // SC_ASYNC: groups in the staging ring (SC_NG - 1 in flight)
-#endif
-#ifndef SC_VOTE_POINT
-#define SC_VOTE_POINT 1               // 1: one screen-failure vote per point; 0: one per register set
-#endif
 #ifndef SC_UT
 #define SC_UT 2                       // loads per thread in the masked register sets of an item's ragged tail (3 spills in the loop)
 #endif
-#ifndef SC_FU
-#define SC_FU 1                       // 128-bit groups of keys read per thread before the first is decoded in the write-out
-                                      // (1 = the plain loop; 2 / 4 measured 0.4 % / 1.4 % slower, r2p)
-#endif
-#ifndef SC_BAND_BRANCHY
-#define SC_BAND_BRANCHY 0
-#endif
-#ifndef SC_LIST_PIPE
-#define SC_LIST_PIPE 0                // 1 (A/B builds): the band passes request list batch k+1 before folding batch k in, and the first
-#endif                                // batch of a band before the write-out in front of it -- 2.6 % SLOWER (1.811 vs 1.765 ms, r2ac)
 #ifndef SC_LU
 #define SC_LU 4                       // 128-bit spill-list loads in flight per lane in pass 2
 #endif
@@ -114,21 +86,6 @@ __device__ __forceinline__ uint4 ld_spill2(const uint2 *p)
     return v;
 }
 
-// 16-byte asynchronous copy global -> shared, past L1 and past the register file (LDGSTS.BYPASS), L2 evict-first
-__device__ __forceinline__ void cp_async16(const uint32_t dst, const void *src, const uint64_t pol)
-{
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds_f4(const uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-
 // max-reduce `key` into the shared-memory cell at `addr` when `doit`: LDS pre-check (most points are not a new maximum)
 // + ATOMS.MAX, predicated instead of branched.
 // `w` is the point's intensity word -- dead data, but it doubles as the destination of the LDS: that keeps its register
@@ -137,13 +94,6 @@ __device__ __forceinline__ float4 lds_f4(const uint32_t addr)
 // the long scoreboard: one POPC held 20 % of all stall samples in profiles/r2d) and defeats the register ping-pong.
 __device__ __forceinline__ void smem_max_if(const uint32_t addr, const uint32_t key, const bool doit, uint32_t w)
 {
-#if SC_NO_PRECHECK                               // (A/B builds: the atomic alone)
-    asm volatile("{\n"
-                 ".reg .pred p;\n"
-                 "setp.ne.u32 p, %3, 0;\n"
-                 "@p red.shared.max.u32 [%1], %2;\n"
-                 "}" : "+r"(w) : "r"(addr), "r"(key), "r"((uint32_t)doit) : "memory");
-#else
     asm volatile("{\n"
                  ".reg .pred p, q;\n"
                  "setp.ne.u32 p, %3, 0;\n"
@@ -151,7 +101,6 @@ __device__ __forceinline__ void smem_max_if(const uint32_t addr, const uint32_t 
                  "setp.gt.and.u32 q, %2, %0, p;\n"
                  "@q red.shared.max.u32 [%1], %2;\n"
                  "}" : "+r"(w) : "r"(addr), "r"(key), "r"((uint32_t)doit) : "memory");
-#endif
 }
 
 __device__ __forceinline__ uint32_t sc_tok3(const float a, const float b, const float c)
@@ -216,9 +165,7 @@ __device__ __forceinline__ void sc_spill(const bool sp, const uint32_t key, cons
                                          const unsigned lt)
 {
     const unsigned m = __ballot_sync(0xffffffffu, sp);
-#ifndef SC_TIMING_NO_SPILL                       // (timing experiments only: wrong grids)
     if (sp) st_spill(reinterpret_cast<uint2 *>(gbase) + (goff + __popc(m & lt)), (uint32_t)cell, key);
-#endif
     goff += __popc(m);
 }
 template <bool SPILL>
@@ -312,10 +259,10 @@ __device__ __forceinline__ void sc_park(const ExactArgs *ea, const float4 v, con
 // One register set -- U points per lane -- called warp-uniformly; the lane's first `mine` points exist (all U in the
 // streaming loop, fewer in the item's last, ragged set).
 // Point by point: screen, commit; then ONE vote per set for the points that failed the screen.
-// (SC_BATCH = 1 screens the U points first as one branch-free block, so that ptxas interleaves the U dependent chains,
-// and commits afterwards: better ILP per warp, but the U (cell, key, valid) triples stay live, predicates get packed
-// into registers and the next set's loads issue later -- measured 6 % slower, profiles/r2_notes.md r2k.  The kernel is
-// short of bytes in flight, not of ILP: fewer, fatter threads (640 x 3, 512 x 4) are slower still.)
+// (Screening the U points first as one branch-free block, so that ptxas interleaves the U dependent chains, and
+// committing afterwards was measured 6 % slower -- the (cell, key, valid) triples stay live, predicates get packed into
+// registers and the next set's loads issue later -- and so was ONE screen vote per set, which removes the branch between
+// the points and lets ptxas interleave them by itself: profiles/r2_notes.md, r2k/r2l.)
 // `qoff`: byte offset of the exact-path queues from the rows; the warp's own queue address and the scan's counter block
 // are only formed on the rare paths.  STATS = false: no per-scan counters are kept at all (stats == NULL).
 template <int VARIANT, bool FULL, bool DEF, bool SPILL, bool STATS, int U>
@@ -326,11 +273,6 @@ __device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, c
 {
     const int S = DEF ? dsc::defgrid::S : cfg.S;
     bool slow[U];
-#if SC_BATCH
-    int cell[U];
-    uint32_t key[U];
-    bool valid[U];
-#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         int ring, sector;
@@ -348,15 +290,6 @@ __device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, c
         }
         const float zv = FULL ? v[u].z : __fadd_rn(v[u].z, cfg.offset);
         slow[u] = active && !ok;
-#if SC_BATCH
-        key[u] = sc_key<FULL>(zv);
-        valid[u] = take && sc_counts<FULL>(zv);
-        cell[u] = ring * S + sector;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) sc_commit<SPILL>(key[u], cell[u], valid[u], sm, gbase, goff, lt, u == 0 ? wtok : 0u);
-#else
-#if SC_VOTE_POINT
         {   // ONE vote per point for "some lane spills or failed the screen": most warps have neither (consecutive points
             // of a beam share their rings; 0.3 % of the points fail the screen)
             const uint32_t key = sc_key<FULL>(zv);
@@ -371,21 +304,7 @@ __device__ __forceinline__ void sc_set(const BinCfg &cfg, const ExactArgs *ea, c
                     sc_park<VARIANT, FULL, SPILL, STATS>(ea, v[u], slow[u], gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
             }
         }
-#else
-        sc_commit<SPILL>(sc_key<FULL>(zv), ring * S + sector, take && sc_counts<FULL>(zv), sm, gbase, goff, lt, u == 0 ? wtok : 0u);
-#endif
     }
-#endif
-#if !SC_VOTE_POINT
-    bool any_slow = slow[0];
-#pragma unroll
-    for (int u = 1; u < U; ++u) any_slow = any_slow || slow[u];
-    if (__any_sync(0xffffffffu, any_slow)) {     // warp-uniform, rare
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            sc_park<VARIANT, FULL, SPILL, STATS>(ea, v[u], slow[u], gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt);
-    }
-#endif
 }
 
 // exact-only flavour (DSC_FLAG_EXACT_ONLY, non-dyadic gaps): every point takes the fdlibm chain
@@ -494,23 +413,13 @@ __device__ __forceinline__ float4 sc_decode4(const uint4 q)
     return f;
 }
 
-// decode `nvec` 128-bit groups of keys from shared memory to floats, re-zeroing the rows (SC_FU > 1: that many groups per
-// thread are read before the first is decoded)
+// decode `nvec` 128-bit groups of keys from shared memory to floats, re-zeroing the rows.  (Reading 2 or 4 groups per
+// thread before the first is decoded was measured 0.4 % / 1.4 % slower than this plain loop, which ptxas unrolls itself.)
 template <int NT, bool FULL>
 __device__ __forceinline__ void sc_flush_rows(uint32_t *__restrict__ srows, float4 *__restrict__ dst, int nvec)
 {
     uint4 *const s4 = reinterpret_cast<uint4 *>(srows);
-    int i = threadIdx.x;
-    for (; i + (SC_FU - 1) * NT < nvec; i += SC_FU * NT) {
-        uint4 q[SC_FU];
-#pragma unroll
-        for (int d = 0; d < SC_FU; ++d) q[d] = s4[i + d * NT];
-#pragma unroll
-        for (int d = 0; d < SC_FU; ++d) s4[i + d * NT] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int d = 0; d < SC_FU; ++d) __stcs(dst + i + d * NT, sc_decode4<FULL>(q[d]));
-    }
-    for (; i < nvec; i += NT) {
+    for (int i = threadIdx.x; i < nvec; i += NT) {
         const uint4 q = s4[i];
         s4[i] = make_uint4(0, 0, 0, 0);
         __stcs(dst + i, sc_decode4<FULL>(q));
@@ -523,23 +432,11 @@ __device__ __forceinline__ void sc_band_entry(const uint32_t cell, const uint32_
                                               const uint32_t lo1, const uint32_t n1, const uint32_t lo2, const uint32_t n2,
                                               const bool present)
 {
-#if SC_BAND_BRANCHY
-    if (!present) return;
-    uint32_t l = cell - lo1;
-    if (l >= n1) {
-        l = cell - lo2;
-        if (l >= n2) return;
-        l += n1;
-    }
-    const uint32_t a = sbase + l * 4u;
-    if (key > lds_u32(a)) reds_max_u32(a, key);
-#else
     // branch-free: both interval tests, one predicated LDS pre-check + ATOMS.MAX
     const uint32_t l1 = cell - lo1, l2 = cell - lo2;
     const bool in1 = l1 < n1, in2 = l2 < n2;
     const uint32_t l = in1 ? l1 : l2 + n1;
     smem_max_if(sbase + l * 4u, key, present && (in1 || in2), 0u);
-#endif
 }
 
 // End of a whole-scan item (this CTA owns the scan): write out the resident rows, then reduce and write out the other
@@ -560,13 +457,6 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
             if (i0 + 64 * d < len) q[d] = ld_spill2(wseg + i0 + 64 * d);
         }
     };
-#if SC_LIST_PIPE
-    // The first batch of a band is requested BEFORE the write-out and the barrier in front of the band (the warp's own
-    // list is complete: only its own lanes append to it), and batch k+1 before batch k is folded in.  Measured slower.
-    uint4 q[SC_LU];
-    __syncwarp();
-    load_batch(q, lane2);
-#endif
     __syncthreads();                             // every shared-memory atomic and every list store of the item is done
     // resident rows: rings r0 .. r0+ns-2, and the clamp ring R-1 kept in row ns-1
     sc_flush_rows<NT, FULL>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
@@ -581,71 +471,21 @@ __device__ __forceinline__ void sc_finish_scan(uint32_t *__restrict__ srows, con
         const uint32_t lo1 = (uint32_t)b0 * (uint32_t)S, n1 = (uint32_t)rows1 * (uint32_t)S;
         const uint32_t lo2 = (uint32_t)ring2 * (uint32_t)S, n2 = (uint32_t)rows2 * (uint32_t)S;
         __syncthreads();                         // the rows are zero again
-#ifndef SC_TIMING_NO_PASS2                       // (timing experiments only: wrong grids)
         for (int i0 = lane2; i0 - lane2 < len; i0 += 64 * SC_LU) {              // warp-uniform trip count
-#if SC_LIST_PIPE
-            uint4 nq[SC_LU];
-            load_batch(nq, i0 + 64 * SC_LU);                                     // (nothing is requested past the end of the list)
-#else
             uint4 q[SC_LU];
             load_batch(q, i0);
-#endif
 #pragma unroll
             for (int d = 0; d < SC_LU; ++d) {
                 const int i = i0 + 64 * d;
                 sc_band_entry(q[d].x, q[d].y, sbase, lo1, n1, lo2, n2, i < len);
                 sc_band_entry(q[d].z, q[d].w, sbase, lo1, n1, lo2, n2, i + 1 < len);
             }
-#if SC_LIST_PIPE
-#pragma unroll
-            for (int d = 0; d < SC_LU; ++d) q[d] = nq[d];
-#endif
         }
-#if SC_LIST_PIPE
-        if (b0 + ns < nv) load_batch(q, lane2);  // first batch of the next band, in flight during this band's write-out
-#endif
-#endif
         __syncthreads();
         sc_flush_rows<NT, FULL>(srows, oq + (size_t)b0 * rowvec, rows1 * rowvec);
         sc_flush_rows<NT, FULL>(srows + (size_t)rows1 * S, oq + (size_t)ring2 * rowvec, rows2 * rowvec);
     }
     __syncthreads();                             // rows are zero before the next scan's atomics
-}
-
-// End of a whole-scan item, SC_SLOT form: the non-resident rings were reduced with RED.MAX on the CTA's private L2 slot
-// (a full key grid, zero == empty); decode resident rows and slot to floats and re-zero both.  Ends with a CTA barrier.
-template <int NT, bool FULL, int DU = 4>
-__device__ __forceinline__ void sc_finish_slot(uint32_t *__restrict__ srows, uint32_t *__restrict__ slot,
-                                               float *__restrict__ out_scan, const int ns, const int r0, const int R, const int S)
-{
-    const int rowvec = S >> 2;
-    float4 *oq = reinterpret_cast<float4 *>(out_scan);
-    __threadfence();                             // our REDs are performed ...
-    __syncthreads();                             // ... before any thread of the CTA reads the keys back
-    sc_flush_rows<NT, FULL>(srows, oq + (size_t)r0 * rowvec, (ns - 1) * rowvec);
-    sc_flush_rows<NT, FULL>(srows + (size_t)(ns - 1) * S, oq + (size_t)(R - 1) * rowvec, rowvec);
-    uint4 *kq = reinterpret_cast<uint4 *>(slot);
-    // rings 0 .. r0-1 and r0+ns-1 .. R-2, as one index range with a jump over the window
-    const int n_lo = r0 * rowvec, n_tot = (R - ns) * rowvec, jump = (ns - 1) * rowvec;
-    for (int j0 = threadIdx.x; j0 < n_tot; j0 += NT * DU) {
-        uint4 q[DU];
-#pragma unroll
-        for (int d = 0; d < DU; ++d) {
-            const int j = j0 + d * NT;
-            if (j < n_tot) q[d] = __ldcg(kq + (j < n_lo ? j : j + jump));
-        }
-#pragma unroll
-        for (int d = 0; d < DU; ++d) {
-            const int j = j0 + d * NT;
-            if (j < n_tot) {
-                const int i = j < n_lo ? j : j + jump;
-                __stcs(oq + i, sc_decode4<FULL>(q[d]));
-                if (q[d].x | q[d].y | q[d].z | q[d].w) __stcg(kq + i, make_uint4(0, 0, 0, 0));
-            }
-        }
-    }
-    __threadfence();                             // the zeroes are performed ...
-    __syncthreads();                             // ... before the next scan's REDs
 }
 
 // End of a split work item: fold the resident rows into the scan's key grid (== its output grid), count the item as
@@ -716,7 +556,7 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
     // per-warp chunk counters, 8 decode loads in flight) spilled inside the loop and lost 15-40 %
     // (profiles/r1_notes.md).
     constexpr int STEP = NT * U;
-    constexpr bool SPILL = !SPLIT && !SC_SLOT;
+    constexpr bool SPILL = !SPLIT;
     extern __shared__ __align__(16) uint32_t smem_raw[];
     __shared__ int s_next[2];
     __shared__ int s_last;
@@ -765,8 +605,6 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             sc_item<SPLIT>(item, offsets, n_scans, sp, scan, parts, p0, n);
             if constexpr (SPLIT) {
                 gbase = reinterpret_cast<uint32_t *>(out + (size_t)scan * cells);
-            } else if constexpr (SC_SLOT) {
-                gbase = reinterpret_cast<uint32_t *>(spill) + (size_t)blockIdx.x * (size_t)cells;
             } else {
                 // the write position counts entries from the start of the launch's spill buffer (host guarantees
                 // gridDim.x * spill_cap < 2^32): the store address is one multiply-add away from it
@@ -778,61 +616,6 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             // one register across the loop instead of a 64-bit pointer
             const float4 *const pts4 = reinterpret_cast<const float4 *>(pts);
             unsigned n_clamped = 0;
-#if SC_ASYNC
-            // The stream goes global -> shared with 16-byte asynchronous copies (LDGSTS.BYPASS: past L1, past the register
-            // file), one point per thread per group, into a ring of SC_NG groups behind the exact-path queues; each thread
-            // reads back only what it copied itself, so cp.async.wait_group is all the synchronisation there is.  SC_NG-1
-            // groups (NT * 16 B each) are in flight at any time, whatever the register budget.
-            {
-                constexpr int NG = SC_NG;
-                constexpr uint32_t GB = (uint32_t)NT * 16u;
-                const uint32_t stg = sm.base + qoff + (FAST ? (uint32_t)(NT / 32) * SCQ_WARP_BYTES : 0u) + (uint32_t)tid * 16u;
-                const int ngroups = (n + NT - 1) / NT;
-                const int nfullg = n / NT;                                     // groups in which every thread has a point
-                int rem = n - tid;                                               // > k * NT  <=>  this thread has a point in group k
-                uint32_t pf = (uint32_t)p0 + (uint32_t)tid;                      // row of this thread's point in the next group to fetch
-#define SC_FETCH(slot, pred)                                                                                    \
-    do {                                                                                                        \
-        if (pred) cp_async16(stg + (uint32_t)(slot) * GB, pts4 + pf, pol_stream);                               \
-        cp_async_commit();                                                                                      \
-        pf += NT;                                                                                               \
-    } while (0)
-#define SC_ONE(vv, act)                                                                                         \
-    do {                                                                                                        \
-        if constexpr (FAST) sc_set<VARIANT, FULL, DEF, SPILL, STATS, 1>(cfg, &s_ea, (vv), (act) ? 1 : 0, gbase, goff, n_clamped, stats, scan, sm, qoff, qcount, lt); \
-        else sc_point_exact<VARIANT, FULL, SPILL>(&s_ea, (vv)[0], (act), gbase, goff, n_clamped, stats, scan, sm, lt); \
-    } while (0)
-#pragma unroll
-                for (int g = 0; g < NG - 1; ++g) SC_FETCH(g, rem > g * NT);
-                int k0 = 0;
-                for (; k0 + 2 * NG - 1 <= nfullg; k0 += NG) {                    // every group touched here is full: no predicates
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        SC_FETCH((g + NG - 1) % NG, true);
-                        cp_async_wait<NG - 1>();
-                        float4 v[1] = {lds_f4(stg + (uint32_t)g * GB)};
-                        SC_ONE(v, true);
-                    }
-                }
-                rem -= k0 * NT;
-                for (; k0 < ngroups; k0 += NG) {                                 // the last groups
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        if (k0 + g < ngroups) {                                  // CTA-uniform
-                            SC_FETCH((g + NG - 1) % NG, rem > (NG - 1) * NT);
-                            cp_async_wait<NG - 1>();
-                            float4 v[1] = {lds_f4(stg + (uint32_t)g * GB)};
-                            const bool act = rem > 0;
-                            rem -= NT;
-                            SC_ONE(v, act);
-                        }
-                    }
-                }
-                cp_async_wait<0>();
-#undef SC_FETCH
-#undef SC_ONE
-            }
-#else
             const int nfull = n / STEP;
             uint32_t p = (uint32_t)p0 + (uint32_t)tid;
             float4 a[U], b[U];
@@ -899,7 +682,6 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
                 }
             }
 #undef SC_LD
-#endif
             unsigned long long *st = STATS ? stats + (int64_t)scan * DSC_STATS_WORDS : nullptr;
             if constexpr (FAST) sc_drain<VARIANT, FULL, SPILL, NT>(&s_ea, gbase, goff, n_clamped, st, sm, qoff, qcount, lt, s_qcnt);
             if (STATS) {
@@ -916,8 +698,6 @@ k1_scan(const uint8_t *__restrict__ pts, const int64_t *__restrict__ offsets, in
             sc_item<SPLIT>(item2, offsets, n_scans, sp, scan, parts, p0, n);
             if constexpr (SPLIT) {
                 sc_finish_split<NT, FULL, SC_DU>(srows, gbase, ns, r0, R, S, scan, parts, sp.done, &s_last);
-            } else if constexpr (SC_SLOT) {
-                sc_finish_slot<NT, FULL, SC_DU>(srows, gbase, out + (size_t)scan * cells, ns, r0, R, S);
             } else {
                 const unsigned seg = (unsigned)((n + NT - 1) / NT + 1) * 32u;
                 const uint32_t w0 = blockIdx.x * (uint32_t)spill_cap + (uint32_t)(tid >> 5) * seg;
