@@ -22,7 +22,6 @@
 // no global atomics, no key slots to read back and re-zero, and no synchronisation between CTAs for whole-scan items.
 // (Round 1 reduced the non-resident rings with RED.MAX on a private L2 slot per CTA: 72 M scattered L2 atomics per
 // launch, a 282 KB read-back + re-zero per scan and 1.2x write traffic from evicted slot lines: profiles/r1_notes.md.)
-constexpr int SC_THREADS = 1024;
 #ifndef SC_DU
 #define SC_DU 4                       // 128-bit L2 loads in flight per thread in the split-mode decode
 #endif
