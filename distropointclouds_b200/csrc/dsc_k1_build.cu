@@ -55,7 +55,12 @@ static int normalize_device(dsc_ctx *ctx, const float *grids, int n, int64_t cel
     if (n <= 0) return DSC_OK;
     if ((cells & 3) == 0 && cells / 4 < 0x7fffffff && ((((uintptr_t)grids) | ((uintptr_t)out)) & 15) == 0) {
         const int ctas = n < ctx->sm_count ? n : ctx->sm_count;
-        k4_fused<<<ctas, K4_THREADS, 0, st>>>(grids, n, (int)(cells / 4), out);
+        // the head of each grid stays in shared memory between the two passes (everything the SM offers)
+        const size_t k4_smem = ((ctx->smem_optin - 1024) / 16) * 16;
+        int keep_vec = (int)(k4_smem / 16);
+        if (keep_vec > (int)(cells / 4)) keep_vec = (int)(cells / 4);
+        DSC_CUDA(ctx, cudaFuncSetAttribute(k4_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem));
+        k4_fused<<<ctas, K4_THREADS, k4_smem, st>>>(grids, n, (int)(cells / 4), out, keep_vec);
         return dsc_check_launch(ctx, "k4_fused");
     }
     if ((size_t)n > ctx->minmax_cap) {
